@@ -1,0 +1,145 @@
+/* qkmps.h -- C ABI of libqkmps.so, the B200-native quantum-kernel MPS engine.
+ *
+ * The reference (mmetcalf14/qml-cutensornet) has no native ABI: its hot path
+ * is Python that calls third-party libraries.  Each entry point below states
+ * which reference interface it replaces (paths relative to the reference
+ * repo).  All functions return 0 on success and a negative qk_status on
+ * failure; qk_last_error() returns a thread-local message.  Host pointers are
+ * borrowed for the duration of the call.  Opaque handles are owned by the
+ * library and released by the matching *_destroy.  There is no CPU fallback:
+ * every compute entry point fails with QK_ERR_CUDA when no sm_100 device is
+ * usable.
+ */
+#ifndef QKMPS_H
+#define QKMPS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QKMPS_VERSION 100
+
+typedef enum {
+  QK_OK = 0,
+  QK_ERR_ARG = -1,       /* bad argument (also: unknown gate -- cpu_backend/kernel_state_ansatz.py:129, KernelPkg.jl:62) */
+  QK_ERR_CUDA = -2,      /* CUDA runtime / launch failure, or no device */
+  QK_ERR_LIMIT = -3,     /* bond dimension above what the shared-memory-resident kernels support */
+  QK_ERR_ALLOC = -4
+} qk_status;
+
+/* gate kinds accepted by the plan compiler: the gate set of KernelPkg/src/KernelPkg.jl:45-64 */
+typedef enum {
+  QK_GATE_H = 0,
+  QK_GATE_RZ = 1,        /* alpha = coeff * x[fa]            (fa < 0: alpha = coeff) */
+  QK_GATE_RX = 2,
+  QK_GATE_XX = 3,        /* alpha = coeff * (1-x[fa])*(1-x[fb])  (fa < 0: alpha = coeff) */
+  QK_GATE_ZZ = 4,
+  QK_GATE_SWAP = 5
+} qk_gate_kind;
+
+/* One symbolic gate; alpha is in half-turns (TKET convention, theta = pi*alpha/2). */
+typedef struct {
+  int32_t kind;          /* qk_gate_kind */
+  int32_t q0, q1;        /* q1 ignored for 1-qubit gates; 2-qubit gates need q1 == q0 + 1 */
+  int32_t fa, fb;        /* feature indices of the angle expression */
+  double coeff;
+} qk_gate;
+
+/* truncation rule */
+typedef enum {
+  QK_TRUNC_ITENSORS = 0, /* relative discarded weight <= cutoff, no renormalisation
+                            (cpu_backend/kernel_state_ansatz.py:262 -> KernelPkg.jl:68 apply(..; cutoff)) */
+  QK_TRUNC_PYTKET = 1    /* kept weight fraction >= 1 - truncation_error, sigma < 1e-16 dropped,
+                            renormalise, track fidelity (gpu_backend/kernel_state_ansatz.py:141-144) */
+} qk_trunc_mode;
+
+typedef struct qk_plan qk_plan;     /* compiled static op schedule of one ansatz (host object) */
+typedef struct qk_batch qk_batch;   /* device-resident batch of simulated MPS */
+
+typedef struct {
+  int32_t n_qubits, n_gates, n_ops, n_ops_2q, n_ops_1q, n_moves;
+  int32_t chi_cap, threads, trunc_mode;
+  int32_t smem_bytes;
+  int64_t state_stride;             /* c128 elements reserved per state in the working store */
+  double trunc_error;
+} qk_plan_info_t;
+
+typedef struct {                    /* one op of the compiled schedule (for tests / inspection) */
+  int32_t kind;                     /* qk_gate_kind, or 16 = move-right, 17 = move-left */
+  int32_t site, fa, fb, dir;
+  double coeff;
+} qk_op_view;
+
+int qk_version(void);
+const char* qk_last_error(void);
+int qk_device_count(int* count);
+
+/* ---- plan: replaces KernelStateAnsatz's circuit + routing and the per-gate bookkeeping of the
+ *      third-party simulators (gpu_backend/kernel_state_ansatz.py:53-90; main.py:21-45,73). ---- */
+int qk_plan_create_gates(int n_qubits, const qk_gate* gates, int n_gates,
+                         int trunc_mode, double trunc_error, int chi_cap, qk_plan** out);
+/* builds H / Rz / routed XXPhase from the ansatz parameters, then compiles it */
+int qk_plan_create_ansatz(int n_qubits, int reps, double gamma, int hadamard_init,
+                          const int32_t* pairs /*[n_pairs][2]*/, int n_pairs,
+                          int trunc_mode, double trunc_error, int chi_cap, qk_plan** out);
+int qk_plan_info(const qk_plan* plan, qk_plan_info_t* info);
+int qk_plan_ops(const qk_plan* plan, qk_op_view* ops, int max_ops);   /* returns number written */
+void qk_plan_destroy(qk_plan* plan);
+
+/* ---- stage 1: replaces simulate(libhandle, circ, MPSxGate, config) per datapoint
+ *      (gpu_backend/kernel_state_ansatz.py:213-231,255-273) and build_and_sim_circ
+ *      (KernelPkg/src/KernelPkg.jl:45-72).  X is row-major [N][ldx] float64. ---- */
+int qk_simulate(const qk_plan* plan, int device, const double* X_host, int N, int ldx, qk_batch** out);
+int qk_simulate_dev(const qk_plan* plan, int device, void* stream, const double* X_dev, int N, int ldx,
+                    qk_batch** out);
+/* last stage-1 kernel time in ms (CUDA events on the launching stream) */
+int qk_batch_sim_ms(const qk_batch* batch, float* ms);
+
+/* ---- MPS handle surface the orchestrator needs (gpu_backend/kernel_state_ansatz.py:223,295-296):
+ *      bond dimensions, byte size, accumulated fidelity.  Any output pointer may be NULL. ---- */
+int qk_batch_size(const qk_batch* batch, int* N, int* n_qubits);
+int qk_batch_info(const qk_batch* batch, int32_t* chi /*[N][n+1]*/, double* fidelity /*[N]*/,
+                  double* trunc_weight /*[N]*/, int64_t* nbytes /*[N]*/, int32_t* flags /*[N]*/,
+                  int32_t* sweeps /*[N]*/);
+/* site tensors of state i, concatenated, each [chi_l][2][chi_r] complex128 row-major */
+int qk_batch_export(const qk_batch* batch, int i, void* host_buf, int64_t buf_bytes);
+/* test hook: upload MPS made elsewhere (same layout as qk_batch_export, states concatenated) */
+int qk_batch_import(int device, int n_qubits, int N, const int32_t* chi /*[N][n+1]*/,
+                    const void* host_tensors, int64_t bytes, qk_batch** out);
+int qk_batch_max_chi(const qk_batch* batch, int32_t* max_chi /*[n+1]*/);
+void qk_batch_destroy(qk_batch* batch);
+
+/* ---- exchange format: replaces pickled MPS send/recv/sendrecv
+ *      (gpu_backend/kernel_state_ansatz.py:346-352,416-419).  A "frag" buffer holds every state
+ *      of a batch in DMMA-fragment order with batch-uniform padded bond dimensions D[n+1]
+ *      (multiples of 8, D[0] = D[n] = 8); it is plain device memory the caller may all-gather. ---- */
+int qk_frag_stride(int n_qubits, const int32_t* D, int64_t* bytes_per_state);
+int qk_batch_pack(const qk_batch* batch, const int32_t* D, void* frag_dev, void* stream);
+
+/* ---- stage 2: replaces x_mps.vdot(y_mps) + |.|^2 (gpu_backend/kernel_state_ansatz.py:380-387) and
+ *      abs(inner(y, x))^2 (KernelPkg/src/KernelPkg.jl:103-109).  K[y][x] = |<psi_y|psi_x>|^2 for the
+ *      listed tiles (row = y in [r0,r1), col = x in [c0,c1)); K_dev is device float64 with leading
+ *      dimension ldk.  symmetric != 0: fragY is ignored (Y = X), only x <= y is computed inside each
+ *      tile and mirrored (cpu_backend/kernel_state_ansatz.py:271-274). ---- */
+int qk_gram_frags(int device, void* stream, int n_qubits,
+                  const int32_t* Dx, const void* fragX, int Nx,
+                  const int32_t* Dy, const void* fragY, int Ny,
+                  const int32_t* tiles /*[n_tiles][4] = r0,r1,c0,c1*/, int n_tiles, int symmetric,
+                  double* K_dev, int64_t ldk, float* ms_out);
+/* CUDA-core FP64 cross-check kernel working on the unpadded stores (any chi <= cap) */
+int qk_gram_store(const qk_batch* X, const qk_batch* Y_or_null, double* K_host, int64_t ldk, float* ms_out);
+
+/* ---- whole path with host buffers on one device: what build_kernel_matrix does per process.
+ *      K_host is [Ny or Nx][ldk]. ---- */
+int qk_gram_host(const qk_plan* plan, int device, const double* X_host, int Nx,
+                 const double* Y_host_or_null, int Ny, int ldx, double* K_host, int64_t ldk);
+
+/* FP64 tensor-core (DMMA m8n8k4) peak microbenchmark: TFLOP/s over `iters` MMAs per warp */
+int qk_dmma_peak(int device, int iters, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QKMPS_H */

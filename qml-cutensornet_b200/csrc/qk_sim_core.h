@@ -1,0 +1,657 @@
+// Stage 1 core: one cooperative group of G threads simulates one datapoint's circuit as an MPS.
+//
+// Replaces what the reference delegates per gate to ITensors.apply (KernelPkg/src/KernelPkg.jl:68)
+// and pytket-cutensornet simulate(.., MPSxGate, ..) (gpu_backend/kernel_state_ansatz.py:221):
+//   * 1-qubit gate      -> multiply into the site tensor
+//   * gauge move        -> Householder QR / LQ of the centre site, factor pushed into the neighbour
+//   * 2-qubit gate      -> contract the site pair with the gate, one-sided Jacobi (Hestenes) SVD in
+//                          shared memory, reference truncation rule, write both sites back
+//
+// The code is written as a sequence of "parallel phases" (QK_PAR_BEGIN .. QK_PAR_END); on the device
+// a phase runs once per thread and ends in __syncthreads(); in the host emulation build
+// (tests/host_emu, test infrastructure only) the same phase is a loop over the G thread ids.
+// Rules that keep both builds equivalent:
+//   - per-thread state never lives across a phase boundary (it is recomputed or kept in shared memory)
+//   - code outside phases is uniform: it only reads shared scalars written before the last barrier
+//   - a shared scalar that is re-written in the very next phase is read, then QK_BARRIER()
+#pragma once
+#include <math.h>
+#include "qk_types.h"
+
+#if defined(__CUDACC__) && !defined(QK_HOST_EMU)
+#define QK_DEV __device__ __forceinline__
+#define QK_PAR_BEGIN(tid) { const int tid = (int)threadIdx.x;
+#define QK_PAR_END } __syncthreads();
+#define QK_BARRIER() __syncthreads()
+#else
+#define QK_DEV inline
+#define QK_PAR_BEGIN(tid) for (int tid = 0; tid < G; ++tid) {
+#define QK_PAR_END }
+#define QK_BARRIER() ((void)0)
+#endif
+
+#ifndef QK_PI
+#define QK_PI 3.14159265358979323846
+#endif
+
+struct SimShared {
+  int rotated;
+  int keep;
+  int hh_skip;
+  int flags;
+  int sweeps;
+  int max_chi;
+  double renorm;
+  double fidelity;
+  double trunc_weight;
+  double f0;
+  c128 z0;
+};
+
+struct SimCtx {
+  const SimParams* P;
+  c128* W;        // region 1: working matrix (column-major)
+  c128* J;        // region 2: staging for site tensors / accumulated rotations / Q
+  double* scr;    // 4*G doubles reduction scratch
+  double* nrm2;   // [rmax]
+  int* order;     // [rmax]
+  c128* gate;     // [16]
+  c128* diag;     // [rmax] diagonal of R (Householder)
+  int* chi;       // [n+1] bond dimensions of the current datapoint
+  double* x;      // [n] features of the current datapoint
+  SimShared* sh;
+  c128* state;    // global: this datapoint's site slots
+};
+
+// bytes of shared memory the core needs for group size G
+QK_HD size_t qk_sim_smem_bytes(int n, int rmax, int G) {
+  size_t wr = (size_t)rmax * rmax;
+  size_t b = 2 * wr * sizeof(c128);         // W, J
+  b += (size_t)4 * G * sizeof(double);      // scr
+  b += (size_t)rmax * sizeof(double);       // nrm2
+  b += 16 * sizeof(c128);                   // gate
+  b += (size_t)rmax * sizeof(c128);         // diag
+  b += (size_t)(n + 1) * sizeof(double);    // x (+pad)
+  b += sizeof(SimShared);
+  b += (size_t)rmax * sizeof(int);          // order
+  b += (size_t)(n + 1) * sizeof(int);       // chi
+  return (b + 15) & ~(size_t)15;
+}
+
+QK_DEV void qk_sim_carve(SimCtx& c, const SimParams* P, unsigned char* smem, int G) {
+  const size_t wr = (size_t)P->rmax * P->rmax;
+  c.P = P;
+  c.W = (c128*)smem;
+  c.J = c.W + wr;
+  c.scr = (double*)(c.J + wr);
+  c.nrm2 = c.scr + 4 * G;
+  c.gate = (c128*)(c.nrm2 + P->rmax + (P->rmax & 1));
+  c.diag = c.gate + 16;
+  c.x = (double*)(c.diag + P->rmax);
+  c.sh = (SimShared*)(c.x + P->n + (P->n & 1));
+  c.order = (int*)(c.sh + 1);
+  c.chi = c.order + P->rmax;
+}
+
+QK_DEV c128* qk_site(const SimCtx& c, int s) { return c.state + c.P->site_off[s]; }
+
+QK_DEV double qk_angle(const QkOp& op, const double* x) {
+  // alpha in half-turns (KernelPkg.jl:9,17,25,35: theta = pi*alpha/2)
+  double alpha;
+  if (op.fa < 0) alpha = op.coeff;
+  else if (op.kind == QK_OP_XX || op.kind == QK_OP_ZZ) alpha = op.coeff * (1.0 - x[op.fa]) * (1.0 - x[op.fb]);
+  else alpha = op.coeff * x[op.fa];
+  return QK_PI * alpha / 2.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1-qubit gates (KernelPkg.jl:8-22 and ITensors "H")
+// ------------------------------------------------------------------------------------------------
+template <int G>
+QK_DEV void qk_op_1q(SimCtx& c, const QkOp& op) {
+  const int s = op.site;
+  const int cl = c.chi[s], cr = c.chi[s + 1];
+  c128 u00, u01, u10, u11;
+  if (op.kind == QK_OP_H) {
+    const double h = 0.70710678118654752440;
+    u00 = cmake(h, 0); u01 = cmake(h, 0); u10 = cmake(h, 0); u11 = cmake(-h, 0);
+  } else {
+    const double th = qk_angle(op, c.x);
+    const double cs = cos(th), sn = sin(th);
+    if (op.kind == QK_OP_RZ) {
+      u00 = cmake(cs, -sn); u01 = cmake(0, 0); u10 = cmake(0, 0); u11 = cmake(cs, sn);
+    } else {  // RX
+      u00 = cmake(cs, 0); u01 = cmake(0, -sn); u10 = cmake(0, -sn); u11 = cmake(cs, 0);
+    }
+  }
+  c128* A = qk_site(c, s);
+  QK_PAR_BEGIN(tid)
+    for (int idx = tid; idx < cl * cr; idx += G) {
+      const int a = idx / cr, b = idx - a * cr;
+      const c128 v0 = A[(a * 2 + 0) * cr + b], v1 = A[(a * 2 + 1) * cr + b];
+      A[(a * 2 + 0) * cr + b] = cadd(cmul(u00, v0), cmul(u01, v1));
+      A[(a * 2 + 1) * cr + b] = cadd(cmul(u10, v0), cmul(u11, v1));
+    }
+  QK_PAR_END
+}
+
+// 4x4 gate [(L,R),(l,r)], first site = more significant bit (KernelPkg.jl:24-42, ITensors "SWAP")
+QK_DEV void qk_build_gate_2q(const QkOp& op, const double* x, c128* g) {
+  for (int i = 0; i < 16; ++i) g[i] = cmake(0, 0);
+  if (op.kind == QK_OP_SWAP) {
+    g[0 * 4 + 0] = g[1 * 4 + 2] = g[2 * 4 + 1] = g[3 * 4 + 3] = cmake(1, 0);
+    return;
+  }
+  const double th = qk_angle(op, x);
+  const double cs = cos(th), sn = sin(th);
+  if (op.kind == QK_OP_XX) {
+    for (int i = 0; i < 4; ++i) { g[i * 4 + i] = cmake(cs, 0); g[i * 4 + (3 - i)] = cmake(0, -sn); }
+  } else {  // ZZ
+    g[0] = cmake(cs, -sn); g[5] = cmake(cs, sn); g[10] = cmake(cs, sn); g[15] = cmake(cs, -sn);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// one-sided Jacobi (Hestenes) on the R x C matrix W (column-major, ld = R); J (C x C) accumulates
+// the rotations:  W_out = W_in * J,  J unitary.  At convergence the columns of W are orthogonal.
+// ------------------------------------------------------------------------------------------------
+QK_DEV bool qk_rr_pair(int i, int r, int Ce, int C, int& p, int& q) {
+  // round-robin tournament: Ce (even) players, round r in [0, Ce-1), pair slot i in [0, Ce/2)
+  const int m = Ce - 1;
+  if (i == 0) { p = m; q = r; }
+  else { p = (r + i) % m; q = (r - i + m) % m; }
+  if (p > q) { const int t = p; p = q; q = t; }
+  return q < C;
+}
+
+template <int G>
+QK_DEV void qk_jacobi(SimCtx& c, int R, int C) {
+  c128* W = c.W;
+  c128* J = c.J;
+  const int ldw = R;
+  const int Ce = (C + 1) & ~1;
+  const int npairs = Ce / 2;
+  const int nrounds = Ce - 1;
+  int tpp = 1;
+  while (tpp * 2 * npairs <= G && tpp * 2 <= R) tpp *= 2;
+  const int pp = G / tpp;
+  const int npass = (npairs + pp - 1) / pp;
+  const double tol2 = c.P->tol * c.P->tol;
+  int sweep = 0;
+  // total weight (Frobenius norm^2) -- invariant under the rotations
+  QK_PAR_BEGIN(tid)
+    double s = 0.0;
+    for (int i = tid; i < R * C; i += G) s += W[i].x * W[i].x + W[i].y * W[i].y;
+    c.scr[tid] = s;
+  QK_PAR_END
+  double total = 0.0;
+  for (int t = 0; t < G; ++t) total += c.scr[t];
+  QK_BARRIER();
+  const double floor2 = 1e-28 * total;
+  if (C >= 2) {
+    for (; sweep < c.P->max_sweeps; ++sweep) {
+      QK_PAR_BEGIN(tid)
+        if (tid == 0) c.sh->rotated = 0;
+      QK_PAR_END
+      for (int r = 0; r < nrounds; ++r) {
+        for (int pass = 0; pass < npass; ++pass) {
+          QK_PAR_BEGIN(tid)
+            const int ps = tid / tpp, sl = tid - ps * tpp;
+            const int i = pass * pp + ps;
+            int p = 0, q = 0;
+            const bool valid = (i < npairs) && qk_rr_pair(i, r, Ce, C, p, q);
+            double a = 0, b = 0, gr = 0, gi = 0;
+            if (valid) {
+              const c128* wp = W + (size_t)p * ldw;
+              const c128* wq = W + (size_t)q * ldw;
+              for (int row = sl; row < R; row += tpp) {
+                const c128 xp = wp[row], xq = wq[row];
+                a += xp.x * xp.x + xp.y * xp.y;
+                b += xq.x * xq.x + xq.y * xq.y;
+                gr += xp.x * xq.x + xp.y * xq.y;   // gamma = conj(xp) * xq
+                gi += xp.x * xq.y - xp.y * xq.x;
+              }
+            }
+            c.scr[4 * tid + 0] = a; c.scr[4 * tid + 1] = b; c.scr[4 * tid + 2] = gr; c.scr[4 * tid + 3] = gi;
+          QK_PAR_END
+          QK_PAR_BEGIN(tid)
+            const int ps = tid / tpp, sl = tid - ps * tpp;
+            const int i = pass * pp + ps;
+            int p = 0, q = 0;
+            const bool valid = (i < npairs) && qk_rr_pair(i, r, Ce, C, p, q);
+            if (valid) {
+              double a = 0, b = 0, gr = 0, gi = 0;
+              for (int t = 0; t < tpp; ++t) {
+                const double* s4 = c.scr + 4 * (ps * tpp + t);
+                a += s4[0]; b += s4[1]; gr += s4[2]; gi += s4[3];
+              }
+              const double g2 = gr * gr + gi * gi;
+              // a column whose weight is < 1e-28 of the total is numerically zero (rank-deficient theta
+              // is the common case); rotating it again only chases rounding noise
+              const bool live = (a > floor2) && (b > floor2);
+              if (live && g2 > tol2 * a * b && g2 > 0.0) {
+                const double gabs = sqrt(g2);
+                const double zeta = (b - a) / (2.0 * gabs);
+                const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                const double cs = 1.0 / sqrt(1.0 + t * t);
+                const double sn = cs * t;
+                const c128 f = cmake(sn * gr / gabs, sn * gi / gabs);   // s * e^{i phi}
+                c128* wp = W + (size_t)p * ldw;
+                c128* wq = W + (size_t)q * ldw;
+                for (int row = sl; row < R; row += tpp) {
+                  const c128 xp = wp[row], xq = wq[row];
+                  // x' = c x - s e^{-i phi} y ;  y' = s e^{i phi} x + c y
+                  wp[row] = csub(cscale(xp, cs), cmulc(xq, f));
+                  wq[row] = cadd(cmul(f, xp), cscale(xq, cs));
+                }
+                c128* jp = J + (size_t)p * C;
+                c128* jq = J + (size_t)q * C;
+                for (int row = sl; row < C; row += tpp) {
+                  const c128 xp = jp[row], xq = jq[row];
+                  jp[row] = csub(cscale(xp, cs), cmulc(xq, f));
+                  jq[row] = cadd(cmul(f, xp), cscale(xq, cs));
+                }
+                if (sl == 0) c.sh->rotated = 1;
+#ifdef QK_EMU_DEBUG
+                if (sl == 0 && sweep > 40) printf("sweep %d r %d pair (%d,%d) a=%.3e b=%.3e |g|=%.3e rel=%.3e zeta=%.3e t=%.3e R=%d C=%d\n", sweep, r, p, q, a, b, gabs, gabs/sqrt(a*b), zeta, t, R, C);
+#endif
+              }
+            }
+          QK_PAR_END
+        }
+      }
+      const int rot = c.sh->rotated;
+      QK_BARRIER();
+      if (!rot) { ++sweep; break; }
+    }
+  }
+  QK_PAR_BEGIN(tid)
+    if (tid == 0) {
+      c.sh->sweeps += sweep;
+      if (C >= 2 && sweep >= c.P->max_sweeps && c.sh->rotated) c.sh->flags |= QK_FLAG_NO_CONVERGE;
+    }
+  QK_PAR_END
+}
+
+// ------------------------------------------------------------------------------------------------
+// truncation decision on the sorted squared column norms (thread 0).  SURVEY.md A.4:
+//   ITensors  NDTensors truncate!: drop from the tail while discarded + p <= cutoff * sum(p)
+//   pytket    drop sigma < value_of_zero, keep the shortest head with numer/denom >= fidelity, renormalise
+// ------------------------------------------------------------------------------------------------
+QK_DEV void qk_truncate(SimCtx& c, int C, int capb) {
+  const SimParams* P = c.P;
+  int k;
+  double renorm = 1.0;
+  if (P->mode == 0) {
+    double total = 0.0;
+    for (int t = 0; t < C; ++t) total += c.nrm2[c.order[t]];
+    double err = 0.0;
+    k = C;
+    if (!(c.nrm2[c.order[0]] > 0.0)) { k = 1; }
+    else {
+      const double scale = (total == 0.0) ? 1.0 : total;
+      while (k > 1 && err + c.nrm2[c.order[k - 1]] <= P->cutoff * scale) { err += c.nrm2[c.order[k - 1]]; --k; }
+      if (k > capb) {
+        c.sh->flags |= QK_FLAG_CAP_HIT;
+        while (k > capb) { err += c.nrm2[c.order[k - 1]]; --k; }
+      }
+      c.sh->trunc_weight += err / scale;
+      c.sh->fidelity *= (1.0 - err / scale);
+    }
+  } else {
+    int m = 0;
+    for (int t = 0; t < C; ++t) if (sqrt(c.nrm2[c.order[t]]) >= P->value_of_zero) ++m;
+    if (m < 1) m = 1;
+    double denom = 0.0;
+    for (int t = 0; t < m; ++t) denom += c.nrm2[c.order[t]];
+    if (!(denom > 0.0)) { k = 1; }
+    else {
+      double numer = 0.0;
+      k = 0;
+      if (P->fidelity_target < 1.0) {
+        while (P->fidelity_target > numer / denom && k < m) { numer += c.nrm2[c.order[k]]; ++k; }
+        if (k < 1) { numer = c.nrm2[c.order[0]]; k = 1; }
+      } else { k = m; numer = denom; }
+      if (k > capb) {
+        c.sh->flags |= QK_FLAG_CAP_HIT;
+        k = capb;
+        numer = 0.0;
+        for (int t = 0; t < k; ++t) numer += c.nrm2[c.order[t]];
+      }
+      const double kept = numer / denom;
+      renorm = sqrt(1.0 / kept);
+      c.sh->fidelity *= kept;
+      c.sh->trunc_weight += (1.0 - kept);
+    }
+  }
+  c.sh->keep = k;
+  c.sh->renorm = renorm;
+  if (k > c.sh->max_chi) c.sh->max_chi = k;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2-qubit gate on sites (k, k+1)
+// ------------------------------------------------------------------------------------------------
+template <int G>
+QK_DEV void qk_op_2q(SimCtx& c, const QkOp& op) {
+  const int k = op.site;
+  const int ca = c.chi[k], cb = c.chi[k + 1], cc = c.chi[k + 2];
+  const int m = 2 * ca, n2 = 2 * cc;
+  const bool transposed = (m < n2);
+  const int R = transposed ? n2 : m;
+  const int C = transposed ? m : n2;
+  const int ldw = R;
+  c128* A = qk_site(c, k);
+  c128* B = qk_site(c, k + 1);
+  c128* As = c.J;
+  c128* Bs = c.J + (size_t)ca * 2 * cb;
+  c128* W = c.W;
+  c128* J = c.J;
+
+  QK_PAR_BEGIN(tid)
+    for (int i = tid; i < ca * 2 * cb; i += G) As[i] = A[i];
+    for (int i = tid; i < cb * 2 * cc; i += G) Bs[i] = B[i];
+    if (tid == 0) qk_build_gate_2q(op, c.x, c.gate);
+  QK_PAR_END
+
+  // theta[(a,L),(R,c)] = sum_{l,r} g[(L,R),(l,r)] sum_b A[a,l,b] B[b,r,c]
+  QK_PAR_BEGIN(tid)
+    for (int idx = tid; idx < ca * cc; idx += G) {
+      const int a = idx / cc, cidx = idx - a * cc;
+      c128 t[4];
+      for (int l = 0; l < 2; ++l)
+        for (int r = 0; r < 2; ++r) {
+          c128 acc = cmake(0, 0);
+          const c128* ap = As + (size_t)(a * 2 + l) * cb;
+          const c128* bp = Bs + (size_t)r * cc + cidx;
+          for (int b = 0; b < cb; ++b) cfma(acc, ap[b], bp[(size_t)b * 2 * cc]);
+          t[l * 2 + r] = acc;
+        }
+      for (int L = 0; L < 2; ++L)
+        for (int Rr = 0; Rr < 2; ++Rr) {
+          c128 acc = cmake(0, 0);
+          const c128* g = c.gate + (L * 2 + Rr) * 4;
+          for (int lr = 0; lr < 4; ++lr) cfma(acc, g[lr], t[lr]);
+          const int row = a * 2 + L, col = Rr * cc + cidx;
+          if (!transposed) W[row + (size_t)col * ldw] = acc;
+          else W[col + (size_t)row * ldw] = cconj(acc);
+        }
+    }
+  QK_PAR_END
+
+  QK_PAR_BEGIN(tid)
+    for (int i = tid; i < C * C; i += G) {
+      const int col = i / C, row = i - col * C;
+      J[i] = cmake(row == col ? 1.0 : 0.0, 0.0);
+    }
+  QK_PAR_END
+
+  qk_jacobi<G>(c, R, C);
+
+  QK_PAR_BEGIN(tid)
+    for (int j = tid; j < C; j += G) {
+      double s = 0.0;
+      const c128* w = W + (size_t)j * ldw;
+      for (int row = 0; row < R; ++row) s += w[row].x * w[row].x + w[row].y * w[row].y;
+      c.nrm2[j] = s;
+    }
+  QK_PAR_END
+  QK_PAR_BEGIN(tid)
+    for (int j = tid; j < C; j += G) {
+      const double v = c.nrm2[j];
+      int rk = 0;
+      for (int i = 0; i < C; ++i) {
+        const double u = c.nrm2[i];
+        rk += (u > v) || (u == v && i < j);
+      }
+      c.order[rk] = j;
+    }
+  QK_PAR_END
+  QK_PAR_BEGIN(tid)
+    if (tid == 0) qk_truncate(c, C, c.P->cap[k + 1]);
+  QK_PAR_END
+
+  const int keep = c.sh->keep;
+  const double renorm = c.sh->renorm;
+  const bool right = (op.dir == QK_DIR_RIGHT);
+  QK_PAR_BEGIN(tid)
+    // left site  [a][L][t]  (m x keep),  right site [t][R][c]  (keep x n2)
+    for (int idx = tid; idx < m * keep; idx += G) {
+      const int row = idx / keep, t = idx - row * keep;
+      const int j = c.order[t];
+      const double sg = sqrt(c.nrm2[j]);
+      const double isg = sg > 0.0 ? 1.0 / sg : 0.0;
+      c128 v;
+      if (!transposed) v = cscale(W[row + (size_t)j * ldw], right ? isg : renorm);        // W = U S
+      else v = cscale(J[row + (size_t)j * C], right ? 1.0 : sg * renorm);                // U = J
+      A[idx] = v;
+    }
+    for (int idx = tid; idx < keep * n2; idx += G) {
+      const int t = idx / n2, col = idx - t * n2;
+      const int j = c.order[t];
+      const double sg = sqrt(c.nrm2[j]);
+      const double isg = sg > 0.0 ? 1.0 / sg : 0.0;
+      c128 v;
+      if (!transposed) v = cscale(cconj(J[col + (size_t)j * C]), right ? sg * renorm : 1.0);   // V^dag = J^dag
+      else v = cscale(cconj(W[col + (size_t)j * ldw]), right ? renorm : isg);                  // S V^dag = W^dag
+      B[idx] = v;
+    }
+    if (tid == 0) c.chi[k + 1] = keep;
+  QK_PAR_END
+}
+
+// ------------------------------------------------------------------------------------------------
+// Householder QR of W (R x C, column-major ld = R): reflectors H_j = I - 2 u_j u_j^dag with u_j stored
+// in column j (rows j..R-1), R factor in the strict upper triangle + c.diag.  Q (R x kk) -> Qm.
+// ------------------------------------------------------------------------------------------------
+template <int G>
+QK_DEV void qk_apply_reflector(SimCtx& c, const c128* u, int len, c128* M, int ldm, int row0, int col0, int ncols) {
+  // M[row0.., col0..col0+ncols) -= 2 u (u^dag M)
+  if (ncols <= 0) return;
+  int tpc = 1;
+  while (tpc * 2 * ncols <= G && tpc * 2 <= len) tpc *= 2;
+  const int cpp = G / tpc;
+  const int npass = (ncols + cpp - 1) / cpp;
+  for (int pass = 0; pass < npass; ++pass) {
+    QK_PAR_BEGIN(tid)
+      const int cs = tid / tpc, sl = tid - cs * tpc;
+      const int col = pass * cpp + cs;
+      double dr = 0, di = 0;
+      if (col < ncols) {
+        const c128* mc = M + (size_t)(col0 + col) * ldm + row0;
+        for (int i = sl; i < len; i += tpc) {
+          const c128 uu = u[i], mm = mc[i];
+          dr += uu.x * mm.x + uu.y * mm.y;   // conj(u) * m
+          di += uu.x * mm.y - uu.y * mm.x;
+        }
+      }
+      c.scr[2 * tid] = dr; c.scr[2 * tid + 1] = di;
+    QK_PAR_END
+    QK_PAR_BEGIN(tid)
+      const int cs = tid / tpc, sl = tid - cs * tpc;
+      const int col = pass * cpp + cs;
+      if (col < ncols) {
+        double dr = 0, di = 0;
+        for (int t = 0; t < tpc; ++t) { dr += c.scr[2 * (cs * tpc + t)]; di += c.scr[2 * (cs * tpc + t) + 1]; }
+        const c128 d2 = cmake(2.0 * dr, 2.0 * di);
+        c128* mc = M + (size_t)(col0 + col) * ldm + row0;
+        for (int i = sl; i < len; i += tpc) mc[i] = csub(mc[i], cmul(u[i], d2));
+      }
+    QK_PAR_END
+  }
+}
+
+template <int G>
+QK_DEV int qk_householder_qr(SimCtx& c, int R, int C, c128* Qm) {
+  c128* W = c.W;
+  const int ldw = R;
+  const int kk = R < C ? R : C;
+  for (int j = 0; j < kk; ++j) {
+    const int len = R - j;
+    c128* col = W + (size_t)j * ldw + j;
+    QK_PAR_BEGIN(tid)
+      double s = 0.0;
+      for (int i = tid; i < len; i += G) s += col[i].x * col[i].x + col[i].y * col[i].y;
+      c.scr[tid] = s;
+    QK_PAR_END
+    QK_PAR_BEGIN(tid)
+      if (tid == 0) {
+        double n2 = 0.0;
+        for (int t = 0; t < G; ++t) n2 += c.scr[t];
+        const c128 alpha = col[0];
+        const double aabs = sqrt(alpha.x * alpha.x + alpha.y * alpha.y);
+        const double nrm = sqrt(n2);
+        if (!(nrm > 0.0) || len == 1) {
+          // nothing to annihilate: H = I, the diagonal entry stays as it is
+          c.sh->hh_skip = 1;
+          c.diag[j] = alpha;
+          c.order[j] = 1;
+        } else {
+          const c128 ph = aabs > 0.0 ? cmake(alpha.x / aabs, alpha.y / aabs) : cmake(1.0, 0.0);
+          c.diag[j] = cmake(-ph.x * nrm, -ph.y * nrm);
+          c.sh->z0 = cmake(alpha.x + ph.x * nrm, alpha.y + ph.y * nrm);
+          c.sh->f0 = 1.0 / sqrt(2.0 * nrm * (nrm + aabs));
+          c.sh->hh_skip = 0;
+          c.order[j] = 0;
+        }
+      }
+    QK_PAR_END
+    if (c.sh->hh_skip) continue;
+    QK_PAR_BEGIN(tid)
+      const double f0 = c.sh->f0;
+      for (int i = tid; i < len; i += G) {
+        const c128 v = (i == 0) ? c.sh->z0 : col[i];
+        col[i] = cscale(v, f0);
+      }
+    QK_PAR_END
+    qk_apply_reflector<G>(c, col, len, W, ldw, j, j + 1, C - 1 - j);
+  }
+  // Q = H_0 H_1 ... H_{kk-1} applied to the first kk columns of the identity
+  QK_PAR_BEGIN(tid)
+    for (int i = tid; i < R * kk; i += G) {
+      const int cidx = i / R, row = i - cidx * R;
+      Qm[i] = cmake(row == cidx ? 1.0 : 0.0, 0.0);
+    }
+  QK_PAR_END
+  for (int j = kk - 1; j >= 0; --j) {
+    if (c.order[j]) continue;
+    qk_apply_reflector<G>(c, W + (size_t)j * ldw + j, R - j, Qm, R, j, j, kk - j);
+  }
+  return kk;
+}
+
+QK_DEV c128 qk_rfactor(const SimCtx& c, int ldw, int t, int b) {
+  if (t < b) return c.W[t + (size_t)b * ldw];
+  if (t == b) return c.diag[t];
+  return cmake(0, 0);
+}
+
+// gauge move: QK_OP_MOVE_R factorises site s as Q R and pushes R into site s+1;
+//             QK_OP_MOVE_L factorises site s as L Q and pushes L into site s-1.
+// (ITensors orthogonalize!, no truncation -- SURVEY.md A.3)
+template <int G>
+QK_DEV void qk_op_move(SimCtx& c, const QkOp& op) {
+  const int s = op.site;
+  const bool to_right = (op.kind == QK_OP_MOVE_R);
+  const int cl = c.chi[s], cr = c.chi[s + 1];
+  const int R = to_right ? 2 * cl : 2 * cr;
+  const int C = to_right ? cr : cl;
+  const int ldw = R;
+  c128* A = qk_site(c, s);
+  c128* W = c.W;
+  QK_PAR_BEGIN(tid)
+    if (to_right) {
+      // W[(a,p), b] = A[a,p,b]
+      for (int i = tid; i < R * C; i += G) {
+        const int row = i / C, b = i - row * C;
+        W[row + (size_t)b * ldw] = A[i];
+      }
+    } else {
+      // W[(p,b), a] = conj(A[a,p,b])
+      for (int i = tid; i < R * C; i += G) {
+        const int a = i / R, pb = i - a * R;
+        W[pb + (size_t)a * ldw] = cconj(A[i]);
+      }
+    }
+  QK_PAR_END
+  c128* Qm = c.J;
+  const int kk = qk_householder_qr<G>(c, R, C, Qm);
+  c128* Nb = c.J + (size_t)R * kk;   // staging for the neighbour site
+  if (to_right) {
+    const int cr2 = c.chi[s + 2];
+    c128* Bn = qk_site(c, s + 1);
+    QK_PAR_BEGIN(tid)
+      for (int i = tid; i < C * 2 * cr2; i += G) Nb[i] = Bn[i];
+      for (int i = tid; i < R * kk; i += G) {          // A[(a,p), t] = Q[(a,p), t]
+        const int row = i / kk, t = i - row * kk;
+        A[i] = Qm[row + (size_t)t * R];
+      }
+    QK_PAR_END
+    QK_PAR_BEGIN(tid)
+      for (int i = tid; i < kk * 2 * cr2; i += G) {    // B'[t, (p,c)] = sum_b R[t,b] B[b,(p,c)]
+        const int t = i / (2 * cr2), pc = i - t * 2 * cr2;
+        c128 acc = cmake(0, 0);
+        for (int b = t; b < C; ++b) cfma(acc, qk_rfactor(c, ldw, t, b), Nb[(size_t)b * 2 * cr2 + pc]);
+        Bn[i] = acc;
+      }
+      if (tid == 0) c.chi[s + 1] = kk;
+    QK_PAR_END
+  } else {
+    const int cl0 = c.chi[s - 1];
+    c128* An = qk_site(c, s - 1);
+    QK_PAR_BEGIN(tid)
+      for (int i = tid; i < cl0 * 2 * C; i += G) Nb[i] = An[i];
+      for (int i = tid; i < kk * R; i += G) {          // A[t,(p,b)] = conj(Q[(p,b), t])
+        const int t = i / R, pb = i - t * R;
+        A[i] = cconj(Qm[pb + (size_t)t * R]);
+      }
+    QK_PAR_END
+    QK_PAR_BEGIN(tid)
+      for (int i = tid; i < cl0 * 2 * kk; i += G) {    // A'[(a',p'), t] = sum_a A[(a',p'), a] conj(R[t,a])
+        const int row = i / kk, t = i - row * kk;
+        c128 acc = cmake(0, 0);
+        for (int a = t; a < C; ++a) cfma(acc, Nb[(size_t)row * C + a], cconj(qk_rfactor(c, ldw, t, a)));
+        An[i] = acc;
+      }
+      if (tid == 0) c.chi[s] = kk;
+    QK_PAR_END
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// whole circuit for datapoint dp
+// ------------------------------------------------------------------------------------------------
+template <int G>
+QK_DEV void qk_sim_datapoint(SimCtx& c, int dp) {
+  const SimParams* P = c.P;
+  const int n = P->n;
+  c.state = P->store + (size_t)dp * P->state_stride;
+  QK_PAR_BEGIN(tid)
+    for (int s = tid; s < n; s += G) {   // |0...0>, KernelPkg.jl:68
+      c128* A = qk_site(c, s);
+      A[0] = cmake(1, 0);
+      A[1] = cmake(0, 0);
+    }
+    for (int b = tid; b <= n; b += G) c.chi[b] = 1;
+    for (int i = tid; i < n; i += G) c.x[i] = P->X[(size_t)dp * P->ldx + i];
+    if (tid == 0) {
+      c.sh->flags = 0; c.sh->sweeps = 0; c.sh->max_chi = 1;
+      c.sh->fidelity = 1.0; c.sh->trunc_weight = 0.0; c.sh->rotated = 0;
+    }
+  QK_PAR_END
+  for (int o = 0; o < P->n_ops; ++o) {
+    const QkOp op = P->ops[o];
+    if (op.kind <= QK_OP_RX) qk_op_1q<G>(c, op);
+    else if (op.kind <= QK_OP_SWAP) qk_op_2q<G>(c, op);
+    else qk_op_move<G>(c, op);
+  }
+  QK_PAR_BEGIN(tid)
+    for (int b = tid; b <= n; b += G) P->chi[(size_t)dp * (n + 1) + b] = c.chi[b];
+    if (tid == 0) {
+      QkStat st;
+      st.fidelity = c.sh->fidelity; st.trunc_weight = c.sh->trunc_weight;
+      st.flags = c.sh->flags; st.sweeps = c.sh->sweeps; st.max_chi = c.sh->max_chi; st.pad = 0;
+      P->stats[dp] = st;
+    }
+  QK_PAR_END
+}

@@ -1,0 +1,91 @@
+// Internal types shared by the plan compiler, the simulation core and the kernels.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define QK_HD __host__ __device__ __forceinline__
+#else
+#define QK_HD inline
+#endif
+
+// complex128 as two doubles; 16-byte aligned so global/shared accesses are 128-bit.
+struct alignas(16) c128 {
+  double x, y;
+};
+
+QK_HD c128 cmake(double x, double y) { c128 r; r.x = x; r.y = y; return r; }
+QK_HD c128 cadd(c128 a, c128 b) { return cmake(a.x + b.x, a.y + b.y); }
+QK_HD c128 csub(c128 a, c128 b) { return cmake(a.x - b.x, a.y - b.y); }
+QK_HD c128 cmul(c128 a, c128 b) { return cmake(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+QK_HD c128 cmulc(c128 a, c128 b) { return cmake(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a * conj(b)
+QK_HD c128 cconj(c128 a) { return cmake(a.x, -a.y); }
+QK_HD c128 cscale(c128 a, double s) { return cmake(a.x * s, a.y * s); }
+QK_HD double cabs2(c128 a) { return a.x * a.x + a.y * a.y; }
+QK_HD void cfma(c128& acc, c128 a, c128 b) {  // acc += a*b
+  acc.x += a.x * b.x - a.y * b.y;
+  acc.y += a.x * b.y + a.y * b.x;
+}
+QK_HD void cfmac(c128& acc, c128 a, c128 b) {  // acc += conj(a)*b
+  acc.x += a.x * b.x + a.y * b.y;
+  acc.y += a.x * b.y - a.y * b.x;
+}
+
+// op kinds of the compiled schedule: gate kinds 0..5 as in qkmps.h, plus gauge moves
+enum {
+  QK_OP_H = 0,
+  QK_OP_RZ = 1,
+  QK_OP_RX = 2,
+  QK_OP_XX = 3,
+  QK_OP_ZZ = 4,
+  QK_OP_SWAP = 5,
+  QK_OP_MOVE_R = 16,  // QR of site `site`, push R into site+1
+  QK_OP_MOVE_L = 17   // LQ of site `site`, push L into site-1
+};
+
+enum { QK_DIR_RIGHT = 0, QK_DIR_LEFT = 1 };
+
+struct QkOp {
+  int32_t kind;
+  int32_t site;   // 1-qubit: the site; 2-qubit: left site k of (k, k+1); move: the site factorised
+  int32_t fa, fb; // feature indices of the angle expression (fa < 0: constant angle)
+  int32_t dir;    // 2-qubit ops: which factor receives the singular values
+  int32_t pad;
+  double coeff;
+};
+
+enum {
+  QK_FLAG_CAP_HIT = 1,      // truncation rule wanted more than the bond cap: extra weight was discarded
+  QK_FLAG_NO_CONVERGE = 2   // Jacobi hit the sweep limit
+};
+
+struct QkStat {
+  double fidelity;      // product of kept weight fractions (pytket mps.fidelity)
+  double trunc_weight;  // sum of relative discarded weights
+  int32_t flags;
+  int32_t sweeps;       // total Jacobi sweeps (profiling)
+  int32_t max_chi;
+  int32_t pad;
+};
+
+struct SimParams {
+  int n;                     // qubits / sites
+  int n_ops;
+  const QkOp* ops;
+  const int32_t* cap;        // [n+1] bond caps (cap[0] = cap[n] = 1)
+  const int64_t* site_off;   // [n+1] offsets (c128 units) of the site slots inside one state
+  int64_t state_stride;      // c128 units per state
+  const double* X;           // [N][ldx]
+  int ldx;
+  int N;
+  c128* store;               // [N][state_stride]
+  int32_t* chi;              // [N][n+1]
+  QkStat* stats;             // [N]
+  int mode;                  // qk_trunc_mode
+  double cutoff;             // ITensors relative cutoff
+  double fidelity_target;    // pytket: 1 - truncation_error
+  double value_of_zero;      // pytket: absolute sigma cutoff
+  double tol;                // Jacobi rotation threshold
+  int max_sweeps;
+  int wr;                    // c128 elements per shared-memory matrix region = (2*capmax)^2
+  int rmax;                  // 2*capmax
+};

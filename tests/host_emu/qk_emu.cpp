@@ -1,0 +1,69 @@
+// TEST INFRASTRUCTURE ONLY: host emulation of the stage-1 device core.
+//
+// Compiles qk_sim_core.h with QK_HOST_EMU so that every "parallel phase" becomes a loop over the
+// thread ids of one cooperative group.  It lets the CPU-only test-suite (-m "not gpu") check the
+// *same source* the CUDA kernel is built from against the oracle: schedule compiler, contraction,
+// Jacobi SVD, truncation rules, Householder gauge moves.  Nothing in the product package loads
+// this library; the product path has no CPU fallback.
+#define QK_HOST_EMU 1
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../qml-cutensornet_b200/csrc/qk_plan.h"
+#include "../../qml-cutensornet_b200/csrc/qk_sim_core.h"
+
+template <int G>
+static void run_group(const SimParams& P, unsigned char* smem, int dp) {
+  SimCtx c;
+  qk_sim_carve(c, &P, smem, G);
+  qk_sim_datapoint<G>(c, dp);
+}
+
+extern "C" {
+
+// Simulate N datapoints.  Outputs: chi [N][n+1], store [N][state_stride] c128 (slots laid out by
+// site_off), stats as 4 doubles per datapoint (fidelity, trunc_weight, flags, sweeps).
+// Returns state_stride (>0) or a negative status.  If store == NULL only returns the stride.
+long long qk_emu_simulate(int n, const qk_gate* gates, int n_gates, int trunc_mode, double trunc_error,
+                          int chi_cap, int force_threads, const double* X, int N, int ldx,
+                          int32_t* chi_out, double* store_out, long long* site_off_out, double* stats_out,
+                          int* n_ops_out, int* n_moves_out) {
+  qk_plan plan;
+  std::string err;
+  int rc = qk_compile_plan(n, gates, n_gates, trunc_mode, trunc_error, chi_cap, &plan, &err);
+  if (rc != 0) return rc;
+  if (n_ops_out) *n_ops_out = (int)plan.ops.size();
+  if (n_moves_out) *n_moves_out = plan.n_moves;
+  if (site_off_out) for (int s = 0; s <= n; ++s) site_off_out[s] = plan.site_off[s];
+  if (!store_out) return plan.state_stride;
+  int G = force_threads > 0 ? force_threads : plan.threads;
+  std::vector<QkStat> stats(N);
+  SimParams P;
+  P.n = n; P.n_ops = (int)plan.ops.size(); P.ops = plan.ops.data(); P.cap = plan.cap.data();
+  P.site_off = plan.site_off.data(); P.state_stride = plan.state_stride;
+  P.X = X; P.ldx = ldx; P.N = N;
+  P.store = (c128*)store_out; P.chi = chi_out; P.stats = stats.data();
+  P.mode = trunc_mode; P.cutoff = trunc_error; P.fidelity_target = 1.0 - trunc_error; P.value_of_zero = 1e-16;
+  P.tol = getenv("QK_EMU_TOL") ? atof(getenv("QK_EMU_TOL")) : 1e-15; P.max_sweeps = getenv("QK_EMU_SWEEPS") ? atoi(getenv("QK_EMU_SWEEPS")) : 60; P.rmax = plan.rmax; P.wr = plan.rmax * plan.rmax;
+  size_t bytes = qk_sim_smem_bytes(n, plan.rmax, G);
+  unsigned char* smem = (unsigned char*)aligned_alloc(64, (bytes + 63) & ~(size_t)63);
+  for (int dp = 0; dp < N; ++dp) {
+    memset(smem, 0xA5, bytes);   // poison: the core must not depend on stale shared memory
+    switch (G) {
+      case 32: run_group<32>(P, smem, dp); break;
+      case 64: run_group<64>(P, smem, dp); break;
+      case 128: run_group<128>(P, smem, dp); break;
+      case 256: run_group<256>(P, smem, dp); break;
+      default: free(smem); return QK_ERR_ARG;
+    }
+    if (stats_out) {
+      stats_out[4 * dp + 0] = stats[dp].fidelity; stats_out[4 * dp + 1] = stats[dp].trunc_weight;
+      stats_out[4 * dp + 2] = stats[dp].flags; stats_out[4 * dp + 3] = stats[dp].sweeps;
+    }
+  }
+  free(smem);
+  return plan.state_stride;
+}
+
+}  // extern "C"
