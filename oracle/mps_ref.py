@@ -223,3 +223,20 @@ def mps_inner(y: RefMPS, x: RefMPS) -> complex:
         t = (e @ ax.reshape(ax.shape[0], 2 * cx)).reshape(ay.shape[0] * 2, cx)     # [(a,p), c']
         e = ay.reshape(ay.shape[0] * 2, cy).conj().T @ t                          # [b', c']
     return complex(e[0, 0])
+
+
+def prepare_for_inner(tensors):
+    """Pre-reshaped operands for repeated overlaps (same arithmetic as ``mps_inner``; only the
+    per-call reshape / conjugate overhead is hoisted so the CPU baseline is not weaker than ITensors,
+    SURVEY.md 8(d))."""
+    ket = [np.ascontiguousarray(a.reshape(a.shape[0], 2 * a.shape[2])) for a in tensors]
+    bra = [np.ascontiguousarray(a.reshape(a.shape[0] * 2, a.shape[2]).conj().T) for a in tensors]
+    dims = [a.shape[2] for a in tensors]
+    return ket, bra, dims
+
+
+def inner_prepared(bra_y, ket_x, dims_x) -> complex:
+    e = np.ones((1, 1), dtype=np.complex128)
+    for ad, ax, cx in zip(bra_y, ket_x, dims_x):
+        e = ad @ (e @ ax).reshape(-1, cx)
+    return complex(e[0, 0])

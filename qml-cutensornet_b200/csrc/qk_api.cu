@@ -1,0 +1,592 @@
+// C ABI of libqkmps.so (declared in include/qkmps.h).  Thin host glue: argument checks, device
+// memory, launches.  No CPU compute path: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "../../include/qkmps.h"
+#include "qk_kernels.cuh"
+#include "qk_plan.h"
+#include "qk_sim_core.h"
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+static int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return QK_ERR_CUDA;
+}
+#define QK_CUDA(call, what)                         \
+  do {                                              \
+    cudaError_t _e = (call);                        \
+    if (_e != cudaSuccess) return cuda_fail(_e, what); \
+  } while (0)
+
+// ---- small caching pool for device blocks: a Gram job allocates the same few large buffers every
+// call (state store, scratch); cudaMalloc/cudaFree of hundreds of MB would otherwise dominate the
+// host side.  Every API call synchronises its stream before returning, so a released block is idle.
+struct PoolBlock { void* p; size_t bytes; int device; };
+static std::vector<PoolBlock> g_pool_free;
+static std::vector<PoolBlock> g_pool_live;
+static size_t g_pool_cached = 0;
+static const size_t kPoolMaxCached = (size_t)8 << 30;
+static std::mutex g_pool_mu;
+
+static cudaError_t pool_alloc(void** out, size_t bytes) {
+  std::lock_guard<std::mutex> lock(g_pool_mu);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (bytes == 0) bytes = 16;
+  int best = -1;
+  for (size_t i = 0; i < g_pool_free.size(); ++i) {
+    const PoolBlock& b = g_pool_free[i];
+    if (b.device == dev && b.bytes >= bytes && b.bytes <= 2 * bytes + 4096 && (best < 0 || b.bytes < g_pool_free[best].bytes))
+      best = (int)i;
+  }
+  if (best >= 0) {
+    PoolBlock b = g_pool_free[best];
+    g_pool_free.erase(g_pool_free.begin() + best);
+    g_pool_cached -= b.bytes;
+    g_pool_live.push_back(b);
+    *out = b.p;
+    return cudaSuccess;
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {   // drop the cache and retry once
+    for (auto& b : g_pool_free) cudaFree(b.p);
+    g_pool_free.clear(); g_pool_cached = 0;
+    cudaGetLastError();
+    e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return e;
+  }
+  g_pool_live.push_back({p, bytes, dev});
+  *out = p;
+  return cudaSuccess;
+}
+
+static void pool_free(void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lock(g_pool_mu);
+  for (size_t i = 0; i < g_pool_live.size(); ++i) {
+    if (g_pool_live[i].p == p) {
+      PoolBlock b = g_pool_live[i];
+      g_pool_live.erase(g_pool_live.begin() + i);
+      if (g_pool_cached + b.bytes <= kPoolMaxCached && g_pool_free.size() < 64) {
+        g_pool_free.push_back(b);
+        g_pool_cached += b.bytes;
+      } else {
+        cudaFree(p);
+      }
+      return;
+    }
+  }
+  cudaFree(p);
+}
+template <typename T>
+static cudaError_t pool_alloc_t(T** out, size_t bytes) { return pool_alloc((void**)out, bytes); }
+
+struct qk_batch {
+  int device = 0;
+  int n = 0, N = 0;
+  int chi_cap = 1;
+  std::vector<int32_t> cap;          // [n+1]
+  std::vector<int64_t> site_off;     // [n+1] c128 units
+  int64_t state_stride = 0;
+  c128* store = nullptr;             // device [N][state_stride]
+  int32_t* chi = nullptr;            // device [N][n+1]
+  QkStat* stats = nullptr;           // device [N]
+  int64_t* site_off_dev = nullptr;   // device [n+1]
+  float sim_ms = 0.f;
+  int sim_grid = 0;
+};
+
+extern "C" {
+
+int qk_version(void) { return QKMPS_VERSION; }
+const char* qk_last_error(void) { return g_err.c_str(); }
+
+int qk_device_count(int* count) {
+  if (!count) return fail(QK_ERR_ARG, "count is NULL");
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) { *count = 0; return cuda_fail(e, "cudaGetDeviceCount"); }
+  *count = c;
+  return QK_OK;
+}
+
+// ---------------------------------------------------------------- plan
+int qk_plan_create_gates(int n_qubits, const qk_gate* gates, int n_gates, int trunc_mode, double trunc_error,
+                         int chi_cap, qk_plan** out) {
+  if (!out) return fail(QK_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  qk_plan* p = new qk_plan();
+  std::string err;
+  int rc = qk_compile_plan(n_qubits, gates, n_gates, trunc_mode, trunc_error, chi_cap, p, &err);
+  if (rc != QK_OK) { delete p; return fail(rc, err); }
+  *out = p;
+  return QK_OK;
+}
+
+int qk_plan_create_ansatz(int n_qubits, int reps, double gamma, int hadamard_init, const int32_t* pairs, int n_pairs,
+                          int trunc_mode, double trunc_error, int chi_cap, qk_plan** out) {
+  if (!out) return fail(QK_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (n_pairs > 0 && !pairs) return fail(QK_ERR_ARG, "pairs is NULL");
+  std::vector<qk_gate> gates;
+  std::string err;
+  int rc = qk_ansatz_gates(n_qubits, reps, gamma, hadamard_init, pairs, n_pairs, &gates, &err);
+  if (rc != QK_OK) return fail(rc, err);
+  return qk_plan_create_gates(n_qubits, gates.data(), (int)gates.size(), trunc_mode, trunc_error, chi_cap, out);
+}
+
+int qk_plan_info(const qk_plan* plan, qk_plan_info_t* info) {
+  if (!plan || !info) return fail(QK_ERR_ARG, "NULL argument");
+  info->n_qubits = plan->n; info->n_gates = plan->n_gates; info->n_ops = (int)plan->ops.size();
+  info->n_ops_2q = plan->n_2q; info->n_ops_1q = plan->n_1q; info->n_moves = plan->n_moves;
+  info->chi_cap = plan->chi_cap; info->threads = plan->threads; info->trunc_mode = plan->trunc_mode;
+  info->smem_bytes = (int32_t)plan->smem_bytes; info->state_stride = plan->state_stride;
+  info->trunc_error = plan->trunc_error;
+  return QK_OK;
+}
+
+int qk_plan_ops(const qk_plan* plan, qk_op_view* ops, int max_ops) {
+  if (!plan || (max_ops > 0 && !ops)) return fail(QK_ERR_ARG, "NULL argument");
+  int k = std::min<int>(max_ops, (int)plan->ops.size());
+  for (int i = 0; i < k; ++i) {
+    const QkOp& o = plan->ops[i];
+    ops[i].kind = o.kind; ops[i].site = o.site; ops[i].fa = o.fa; ops[i].fb = o.fb; ops[i].dir = o.dir; ops[i].coeff = o.coeff;
+  }
+  return k;
+}
+
+void qk_plan_destroy(qk_plan* plan) { delete plan; }
+
+// ---------------------------------------------------------------- batches
+void qk_batch_destroy(qk_batch* b) {
+  if (!b) return;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(b->device);
+  pool_free(b->store); pool_free(b->chi); pool_free(b->stats); pool_free(b->site_off_dev);
+  cudaSetDevice(prev);
+  delete b;
+}
+
+static int batch_alloc(qk_batch* b) {
+  QK_CUDA(cudaSetDevice(b->device), "cudaSetDevice");
+  const size_t nstate = (size_t)std::max(b->N, 1);
+  QK_CUDA(pool_alloc_t(&b->store, nstate * b->state_stride * sizeof(c128)), "cudaMalloc(store)");
+  QK_CUDA(pool_alloc_t(&b->chi, nstate * (b->n + 1) * sizeof(int32_t)), "cudaMalloc(chi)");
+  QK_CUDA(pool_alloc_t(&b->stats, nstate * sizeof(QkStat)), "cudaMalloc(stats)");
+  QK_CUDA(pool_alloc_t(&b->site_off_dev, (b->n + 1) * sizeof(int64_t)), "cudaMalloc(site_off)");
+  QK_CUDA(cudaMemcpy(b->site_off_dev, b->site_off.data(), (b->n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice),
+          "cudaMemcpy(site_off)");
+  return QK_OK;
+}
+
+int qk_simulate_dev(const qk_plan* plan, int device, void* stream_v, const double* X_dev, int N, int ldx,
+                    qk_batch** out) {
+  if (!plan || !out) return fail(QK_ERR_ARG, "NULL argument");
+  *out = nullptr;
+  if (N < 0 || (N > 0 && !X_dev) || ldx < plan->n) return fail(QK_ERR_ARG, "bad X / N / ldx (ldx must be >= n_qubits)");
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  qk_batch* b = new qk_batch();
+  b->device = device; b->n = plan->n; b->N = N; b->chi_cap = plan->chi_cap;
+  b->cap = plan->cap; b->site_off = plan->site_off; b->state_stride = plan->state_stride;
+  int rc = batch_alloc(b);
+  if (rc != QK_OK) { qk_batch_destroy(b); return rc; }
+  if (N == 0) { *out = b; return QK_OK; }
+
+  QkOp* ops_dev = nullptr; int32_t* cap_dev = nullptr; int* counter = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  auto cleanup = [&]() {
+    pool_free(ops_dev); pool_free(cap_dev); pool_free(counter);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+  };
+#define QK_TRY(call, what)                                              \
+  do {                                                                  \
+    cudaError_t _e = (call);                                            \
+    if (_e != cudaSuccess) { cleanup(); qk_batch_destroy(b); return cuda_fail(_e, what); } \
+  } while (0)
+  const size_t nops = plan->ops.size();
+  QK_TRY(pool_alloc_t(&ops_dev, std::max<size_t>(nops, 1) * sizeof(QkOp)), "cudaMalloc(ops)");
+  QK_TRY(pool_alloc_t(&cap_dev, (plan->n + 1) * sizeof(int32_t)), "cudaMalloc(cap)");
+  QK_TRY(pool_alloc_t(&counter, sizeof(int)), "cudaMalloc(counter)");
+  QK_TRY(cudaMemcpyAsync(ops_dev, plan->ops.data(), nops * sizeof(QkOp), cudaMemcpyHostToDevice, stream), "copy ops");
+  QK_TRY(cudaMemcpyAsync(cap_dev, plan->cap.data(), (plan->n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, stream), "copy cap");
+
+  SimParams P;
+  P.n = plan->n; P.n_ops = (int)nops; P.ops = ops_dev; P.cap = cap_dev; P.site_off = b->site_off_dev;
+  P.state_stride = plan->state_stride; P.X = X_dev; P.ldx = ldx; P.N = N;
+  P.store = b->store; P.chi = b->chi; P.stats = b->stats;
+  P.mode = plan->trunc_mode; P.cutoff = plan->trunc_error; P.fidelity_target = 1.0 - plan->trunc_error;
+  P.value_of_zero = 1e-16;   // pytket-cutensornet Config default
+  P.tol = 1e-15; P.max_sweeps = 60; P.rmax = plan->rmax; P.wr = plan->rmax * plan->rmax;
+
+  QK_TRY(cudaEventCreate(&e0), "cudaEventCreate");
+  QK_TRY(cudaEventCreate(&e1), "cudaEventCreate");
+  QK_TRY(cudaEventRecord(e0, stream), "cudaEventRecord");
+  QK_TRY(qk_launch_sim(P, plan->threads, plan->smem_bytes, counter, stream, &b->sim_grid), "stage-1 kernel launch");
+  QK_TRY(cudaEventRecord(e1, stream), "cudaEventRecord");
+  QK_TRY(cudaEventSynchronize(e1), "stage-1 kernel");
+  cudaEventElapsedTime(&b->sim_ms, e0, e1);
+  cleanup();
+#undef QK_TRY
+  *out = b;
+  return QK_OK;
+}
+
+int qk_simulate(const qk_plan* plan, int device, const double* X_host, int N, int ldx, qk_batch** out) {
+  if (!plan || !out) return fail(QK_ERR_ARG, "NULL argument");
+  *out = nullptr;
+  if (N < 0 || (N > 0 && !X_host) || ldx < plan->n) return fail(QK_ERR_ARG, "bad X / N / ldx (ldx must be >= n_qubits)");
+  QK_CUDA(cudaSetDevice(device), "cudaSetDevice");
+  double* X_dev = nullptr;
+  const size_t bytes = (size_t)std::max(N, 1) * ldx * sizeof(double);
+  QK_CUDA(pool_alloc_t(&X_dev, bytes), "cudaMalloc(X)");
+  cudaError_t e = cudaMemcpy(X_dev, X_host, (size_t)N * ldx * sizeof(double), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { pool_free(X_dev); return cuda_fail(e, "cudaMemcpy(X)"); }
+  int rc = qk_simulate_dev(plan, device, nullptr, X_dev, N, ldx, out);
+  pool_free(X_dev);
+  return rc;
+}
+
+int qk_batch_sim_ms(const qk_batch* b, float* ms) {
+  if (!b || !ms) return fail(QK_ERR_ARG, "NULL argument");
+  *ms = b->sim_ms;
+  return QK_OK;
+}
+
+int qk_batch_size(const qk_batch* b, int* N, int* n_qubits) {
+  if (!b) return fail(QK_ERR_ARG, "NULL batch");
+  if (N) *N = b->N;
+  if (n_qubits) *n_qubits = b->n;
+  return QK_OK;
+}
+
+int qk_batch_info(const qk_batch* b, int32_t* chi, double* fidelity, double* trunc_weight, int64_t* nbytes,
+                  int32_t* flags, int32_t* sweeps) {
+  if (!b) return fail(QK_ERR_ARG, "NULL batch");
+  if (b->N == 0) return QK_OK;
+  QK_CUDA(cudaSetDevice(b->device), "cudaSetDevice");
+  std::vector<int32_t> h_chi((size_t)b->N * (b->n + 1));
+  QK_CUDA(cudaMemcpy(h_chi.data(), b->chi, h_chi.size() * sizeof(int32_t), cudaMemcpyDeviceToHost), "copy chi");
+  if (chi) memcpy(chi, h_chi.data(), h_chi.size() * sizeof(int32_t));
+  if (nbytes) {
+    for (int i = 0; i < b->N; ++i) {
+      int64_t t = 0;
+      const int32_t* c = &h_chi[(size_t)i * (b->n + 1)];
+      for (int s = 0; s < b->n; ++s) t += (int64_t)c[s] * 2 * c[s + 1] * 16;   // sum of tensors[k].nbytes (gpu:295)
+      nbytes[i] = t;
+    }
+  }
+  if (fidelity || trunc_weight || flags || sweeps) {
+    std::vector<QkStat> st(b->N);
+    QK_CUDA(cudaMemcpy(st.data(), b->stats, st.size() * sizeof(QkStat), cudaMemcpyDeviceToHost), "copy stats");
+    for (int i = 0; i < b->N; ++i) {
+      if (fidelity) fidelity[i] = st[i].fidelity;
+      if (trunc_weight) trunc_weight[i] = st[i].trunc_weight;
+      if (flags) flags[i] = st[i].flags;
+      if (sweeps) sweeps[i] = st[i].sweeps;
+    }
+  }
+  return QK_OK;
+}
+
+int qk_batch_export(const qk_batch* b, int i, void* host_buf, int64_t buf_bytes) {
+  if (!b || !host_buf) return fail(QK_ERR_ARG, "NULL argument");
+  if (i < 0 || i >= b->N) return fail(QK_ERR_ARG, "state index out of range");
+  QK_CUDA(cudaSetDevice(b->device), "cudaSetDevice");
+  std::vector<int32_t> c(b->n + 1);
+  QK_CUDA(cudaMemcpy(c.data(), b->chi + (size_t)i * (b->n + 1), c.size() * sizeof(int32_t), cudaMemcpyDeviceToHost), "copy chi");
+  int64_t need = 0;
+  for (int s = 0; s < b->n; ++s) need += (int64_t)c[s] * 2 * c[s + 1] * 16;
+  if (buf_bytes < need) return fail(QK_ERR_ARG, "export buffer too small");
+  char* dst = (char*)host_buf;
+  for (int s = 0; s < b->n; ++s) {
+    const size_t bytes = (size_t)c[s] * 2 * c[s + 1] * 16;
+    QK_CUDA(cudaMemcpy(dst, b->store + (size_t)i * b->state_stride + b->site_off[s], bytes, cudaMemcpyDeviceToHost), "copy site");
+    dst += bytes;
+  }
+  return QK_OK;
+}
+
+int qk_batch_import(int device, int n_qubits, int N, const int32_t* chi, const void* host_tensors, int64_t bytes,
+                    qk_batch** out) {
+  if (!out) return fail(QK_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (n_qubits < 1 || N < 1 || !chi || !host_tensors) return fail(QK_ERR_ARG, "bad arguments");
+  qk_batch* b = new qk_batch();
+  b->device = device; b->n = n_qubits; b->N = N;
+  b->cap.assign(n_qubits + 1, 1);
+  for (int i = 0; i < N; ++i)
+    for (int s = 0; s <= n_qubits; ++s) {
+      const int32_t c = chi[(size_t)i * (n_qubits + 1) + s];
+      if (c < 1) { delete b; return fail(QK_ERR_ARG, "bond dimensions must be >= 1"); }
+      b->cap[s] = std::max(b->cap[s], c);
+    }
+  b->chi_cap = *std::max_element(b->cap.begin(), b->cap.end());
+  b->site_off.assign(n_qubits + 1, 0);
+  for (int s = 0; s < n_qubits; ++s) b->site_off[s + 1] = b->site_off[s] + (int64_t)b->cap[s] * 2 * b->cap[s + 1];
+  b->state_stride = b->site_off[n_qubits];
+  int rc = batch_alloc(b);
+  if (rc != QK_OK) { qk_batch_destroy(b); return rc; }
+  std::vector<c128> host((size_t)N * b->state_stride);
+  const char* src = (const char*)host_tensors;
+  int64_t used = 0;
+  for (int i = 0; i < N; ++i)
+    for (int s = 0; s < n_qubits; ++s) {
+      const int32_t* c = chi + (size_t)i * (n_qubits + 1);
+      const int64_t sz = (int64_t)c[s] * 2 * c[s + 1] * 16;
+      if (used + sz > bytes) { qk_batch_destroy(b); return fail(QK_ERR_ARG, "tensor buffer too small"); }
+      memcpy(&host[(size_t)i * b->state_stride + b->site_off[s]], src + used, sz);
+      used += sz;
+    }
+  cudaError_t e = cudaMemcpy(b->store, host.data(), host.size() * sizeof(c128), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(b->chi, chi, (size_t)N * (n_qubits + 1) * sizeof(int32_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(b->stats, 0, (size_t)N * sizeof(QkStat));
+  if (e != cudaSuccess) { qk_batch_destroy(b); return cuda_fail(e, "upload"); }
+  *out = b;
+  return QK_OK;
+}
+
+int qk_batch_max_chi(const qk_batch* b, int32_t* max_chi) {
+  if (!b || !max_chi) return fail(QK_ERR_ARG, "NULL argument");
+  for (int s = 0; s <= b->n; ++s) max_chi[s] = 1;
+  if (b->N == 0) return QK_OK;
+  QK_CUDA(cudaSetDevice(b->device), "cudaSetDevice");
+  std::vector<int32_t> h((size_t)b->N * (b->n + 1));
+  QK_CUDA(cudaMemcpy(h.data(), b->chi, h.size() * sizeof(int32_t), cudaMemcpyDeviceToHost), "copy chi");
+  for (int i = 0; i < b->N; ++i)
+    for (int s = 0; s <= b->n; ++s) max_chi[s] = std::max(max_chi[s], h[(size_t)i * (b->n + 1) + s]);
+  return QK_OK;
+}
+
+// ---------------------------------------------------------------- frag exchange format
+static int check_D(int n, const int32_t* D) {
+  if (!D) return fail(QK_ERR_ARG, "D is NULL");
+  for (int s = 0; s <= n; ++s)
+    if (D[s] < 8 || (D[s] & 7)) return fail(QK_ERR_ARG, "padded bond dimensions must be positive multiples of 8");
+  return QK_OK;
+}
+
+int qk_frag_stride(int n_qubits, const int32_t* D, int64_t* bytes_per_state) {
+  if (n_qubits < 1 || !bytes_per_state) return fail(QK_ERR_ARG, "bad arguments");
+  int rc = check_D(n_qubits, D);
+  if (rc != QK_OK) return rc;
+  FragLayout L;
+  qk_frag_layout(n_qubits, D, &L, nullptr);
+  *bytes_per_state = L.stride_bytes;
+  return QK_OK;
+}
+
+int qk_batch_pack(const qk_batch* b, const int32_t* D, void* frag_dev, void* stream_v) {
+  if (!b || !frag_dev) return fail(QK_ERR_ARG, "NULL argument");
+  int rc = check_D(b->n, D);
+  if (rc != QK_OK) return rc;
+  if (b->N == 0) return QK_OK;
+  QK_CUDA(cudaSetDevice(b->device), "cudaSetDevice");
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  std::vector<int32_t> mc(b->n + 1);
+  rc = qk_batch_max_chi(b, mc.data());
+  if (rc != QK_OK) return rc;
+  for (int s = 0; s <= b->n; ++s)
+    if (mc[s] > D[s]) return fail(QK_ERR_ARG, "padded bond dimension smaller than a state's bond dimension");
+  FragLayout L;
+  std::vector<int64_t> off(b->n + 1);
+  qk_frag_layout(b->n, D, &L, off.data());
+  int32_t* D_dev = nullptr; int64_t* off_dev = nullptr;
+  QK_CUDA(pool_alloc_t(&D_dev, (b->n + 1) * sizeof(int32_t)), "cudaMalloc(D)");
+  cudaError_t e = pool_alloc_t(&off_dev, (b->n + 1) * sizeof(int64_t));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(D_dev, D, (b->n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(off_dev, off.data(), (b->n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess)
+    e = qk_launch_pack(b->n, b->N, b->store, b->state_stride, b->site_off_dev, b->chi, D_dev, off_dev, L.stride_bytes,
+                       L.data_bytes, frag_dev, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  pool_free(D_dev); pool_free(off_dev);
+  if (e != cudaSuccess) return cuda_fail(e, "pack kernel");
+  return QK_OK;
+}
+
+// ---------------------------------------------------------------- stage 2
+int qk_gram_frags(int device, void* stream_v, int n_qubits, const int32_t* Dx, const void* fragX, int Nx,
+                  const int32_t* Dy, const void* fragY, int Ny, const int32_t* tiles, int n_tiles, int symmetric,
+                  double* K_dev, int64_t ldk, float* ms_out) {
+  if (n_qubits < 1 || !fragX || Nx < 1 || !K_dev || n_tiles < 0 || (n_tiles > 0 && !tiles))
+    return fail(QK_ERR_ARG, "bad arguments");
+  if (symmetric) { Dy = Dx; fragY = fragX; Ny = Nx; }
+  if (!fragY || Ny < 1) return fail(QK_ERR_ARG, "bad Y arguments");
+  int rc = check_D(n_qubits, Dx);
+  if (rc == QK_OK) rc = check_D(n_qubits, Dy);
+  if (rc != QK_OK) return rc;
+  if (ldk < Nx) return fail(QK_ERR_ARG, "ldk must be >= Nx");
+  int maxD = 8;
+  for (int s = 0; s <= n_qubits; ++s) maxD = std::max(maxD, std::max(Dx[s], Dy[s]));
+  if (maxD > 16) return fail(QK_ERR_LIMIT, "tensor-core overlap kernel supports padded bond dimensions <= 16");
+  QK_CUDA(cudaSetDevice(device), "cudaSetDevice");
+  cudaStream_t stream = (cudaStream_t)stream_v;
+
+  int TI = 0, TJ = 0;
+  qk_gram_dmma_tile_shape(&TI, &TJ);
+  std::vector<int4> cta;
+  for (int t = 0; t < n_tiles; ++t) {
+    const int r0 = tiles[4 * t], r1 = tiles[4 * t + 1], c0 = tiles[4 * t + 2], c1 = tiles[4 * t + 3];
+    if (r0 < 0 || c0 < 0 || r1 > Ny || c1 > Nx || r0 > r1 || c0 > c1) return fail(QK_ERR_ARG, "tile out of range");
+    for (int y0 = r0; y0 < r1; y0 += TJ)
+      for (int x0 = c0; x0 < c1; x0 += TI) {
+        const int ye = std::min(y0 + TJ, r1), xe = std::min(x0 + TI, c1);
+        if (symmetric && x0 > ye - 1) continue;   // whole sub-tile above the diagonal
+        cta.push_back(make_int4(y0, x0, ye, xe));
+      }
+  }
+  if (cta.empty()) { if (ms_out) *ms_out = 0.f; return QK_OK; }
+
+  FragLayout Lx, Ly;
+  std::vector<int64_t> offx(n_qubits + 1), offy(n_qubits + 1);
+  qk_frag_layout(n_qubits, Dx, &Lx, offx.data());
+  qk_frag_layout(n_qubits, Dy, &Ly, offy.data());
+  int slot_x = 0, slot_y = 0;
+  for (int s = 0; s < n_qubits; ++s) {
+    slot_x = std::max(slot_x, Dx[s] * Dx[s + 1] * 32);
+    slot_y = std::max(slot_y, Dy[s] * Dy[s + 1] * 32);
+  }
+
+  // one device scratch block: Dx, Dy, offx, offy, tiles
+  const size_t nb = (size_t)(n_qubits + 1);
+  const size_t bytes_i = 2 * nb * sizeof(int32_t), bytes_o = 2 * nb * sizeof(int64_t), bytes_t = cta.size() * sizeof(int4);
+  const size_t o_off = (bytes_i + 15) & ~(size_t)15, t_off = (o_off + bytes_o + 15) & ~(size_t)15;
+  std::vector<unsigned char> hbuf(t_off + bytes_t);
+  memcpy(hbuf.data(), Dx, nb * sizeof(int32_t));
+  memcpy(hbuf.data() + nb * sizeof(int32_t), Dy, nb * sizeof(int32_t));
+  memcpy(hbuf.data() + o_off, offx.data(), nb * sizeof(int64_t));
+  memcpy(hbuf.data() + o_off + nb * sizeof(int64_t), offy.data(), nb * sizeof(int64_t));
+  memcpy(hbuf.data() + t_off, cta.data(), bytes_t);
+  unsigned char* dbuf = nullptr;
+  QK_CUDA(pool_alloc_t(&dbuf, hbuf.size()), "cudaMalloc(gram scratch)");
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaError_t e = cudaMemcpyAsync(dbuf, hbuf.data(), hbuf.size(), cudaMemcpyHostToDevice, stream);
+  GramParams P;
+  P.n = n_qubits;
+  P.Dx = (const int32_t*)dbuf; P.Dy = P.Dx + nb;
+  P.offx = (const int64_t*)(dbuf + o_off); P.offy = P.offx + nb;
+  P.fragX = (const unsigned char*)fragX; P.fragY = (const unsigned char*)fragY;
+  P.strideX = Lx.stride_bytes; P.strideY = Ly.stride_bytes; P.dataX = Lx.data_bytes; P.dataY = Ly.data_bytes;
+  P.Nx = Nx; P.Ny = Ny;
+  P.tiles = (const int4*)(dbuf + t_off); P.n_cta_tiles = (int)cta.size();
+  P.symmetric = symmetric ? 1 : 0;
+  P.K = K_dev; P.ldk = ldk; P.slot_x = slot_x; P.slot_y = slot_y;
+  if (e == cudaSuccess) e = cudaEventCreate(&e0);
+  if (e == cudaSuccess) e = cudaEventCreate(&e1);
+  if (e == cudaSuccess) e = cudaEventRecord(e0, stream);
+  if (e == cudaSuccess) e = qk_launch_gram_dmma(P, maxD, stream);
+  if (e == cudaSuccess) e = cudaEventRecord(e1, stream);
+  if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+  float ms = 0.f;
+  if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  pool_free(dbuf);
+  if (e != cudaSuccess) return cuda_fail(e, "stage-2 kernel");
+  if (ms_out) *ms_out = ms;
+  return QK_OK;
+}
+
+int qk_gram_store(const qk_batch* X, const qk_batch* Y, double* K_host, int64_t ldk, float* ms_out) {
+  if (!X || !K_host) return fail(QK_ERR_ARG, "NULL argument");
+  if (!Y) Y = X;
+  if (X->n != Y->n || X->device != Y->device) return fail(QK_ERR_ARG, "batches do not match");
+  if (ldk < X->N) return fail(QK_ERR_ARG, "ldk must be >= Nx");
+  if (X->N == 0 || Y->N == 0) return QK_OK;
+  QK_CUDA(cudaSetDevice(X->device), "cudaSetDevice");
+  double* K_dev = nullptr;
+  QK_CUDA(pool_alloc_t(&K_dev, (size_t)Y->N * X->N * sizeof(double)), "cudaMalloc(K)");
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, 0);
+  cudaError_t e = qk_launch_gram_store(X->n, X->store, X->state_stride, X->site_off_dev, X->chi, X->chi_cap, X->N,
+                                       Y->store, Y->state_stride, Y->site_off_dev, Y->chi, Y->chi_cap, Y->N, K_dev,
+                                       X->N, 0);
+  cudaEventRecord(e1, 0);
+  if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+  float ms = 0.f;
+  if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (e == cudaSuccess)
+    e = cudaMemcpy2D(K_host, ldk * sizeof(double), K_dev, X->N * sizeof(double), X->N * sizeof(double), Y->N,
+                     cudaMemcpyDeviceToHost);
+  pool_free(K_dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cross-check Gram kernel");
+  if (ms_out) *ms_out = ms;
+  return QK_OK;
+}
+
+// ---------------------------------------------------------------- whole path, host buffers
+int qk_gram_host(const qk_plan* plan, int device, const double* X_host, int Nx, const double* Y_host, int Ny, int ldx,
+                 double* K_host, int64_t ldk) {
+  if (!plan || !X_host || !K_host || Nx < 1) return fail(QK_ERR_ARG, "bad arguments");
+  const bool sym = (Y_host == nullptr);
+  if (!sym && Ny < 1) return fail(QK_ERR_ARG, "bad Ny");
+  if (ldk < Nx) return fail(QK_ERR_ARG, "ldk must be >= Nx");
+  qk_batch *bx = nullptr, *by = nullptr;
+  int rc = qk_simulate(plan, device, X_host, Nx, ldx, &bx);
+  if (rc == QK_OK && !sym) rc = qk_simulate(plan, device, Y_host, Ny, ldx, &by);
+  void *fx = nullptr, *fy = nullptr;
+  double* K_dev = nullptr;
+  const int n = plan->n;
+  const int rows = sym ? Nx : Ny;
+  std::vector<int32_t> Dx(n + 1), Dy(n + 1);
+  auto padded = [&](qk_batch* b, std::vector<int32_t>& D) {
+    int r = qk_batch_max_chi(b, D.data());
+    for (int s = 0; s <= n; ++s) D[s] = (D[s] + 7) & ~7;
+    return r;
+  };
+  if (rc == QK_OK) rc = padded(bx, Dx);
+  if (rc == QK_OK && !sym) rc = padded(by, Dy);
+  int maxD = 8;
+  if (rc == QK_OK) {
+    for (int s = 0; s <= n; ++s) maxD = std::max(maxD, std::max(Dx[s], sym ? 8 : Dy[s]));
+  }
+  if (rc == QK_OK && maxD > 16) {
+    // bond dimensions above the tensor-core kernel's register budget: CUDA-core kernel
+    rc = qk_gram_store(bx, sym ? nullptr : by, K_host, ldk, nullptr);
+  } else if (rc == QK_OK) {
+    int64_t sx = 0, sy = 0;
+    qk_frag_stride(n, Dx.data(), &sx);
+    if (!sym) qk_frag_stride(n, Dy.data(), &sy);
+    cudaError_t e = pool_alloc(&fx, (size_t)sx * Nx);
+    if (e == cudaSuccess && !sym) e = pool_alloc(&fy, (size_t)sy * Ny);
+    if (e == cudaSuccess) e = pool_alloc_t(&K_dev, (size_t)rows * Nx * sizeof(double));
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaMalloc(frag/K)");
+    if (rc == QK_OK) rc = qk_batch_pack(bx, Dx.data(), fx, nullptr);
+    if (rc == QK_OK && !sym) rc = qk_batch_pack(by, Dy.data(), fy, nullptr);
+    const int32_t tile[4] = {0, rows, 0, Nx};
+    if (rc == QK_OK)
+      rc = qk_gram_frags(device, nullptr, n, Dx.data(), fx, Nx, sym ? nullptr : Dy.data(), fy, Ny, tile, 1, sym ? 1 : 0,
+                         K_dev, Nx, nullptr);
+    if (rc == QK_OK) {
+      e = cudaMemcpy2D(K_host, ldk * sizeof(double), K_dev, Nx * sizeof(double), Nx * sizeof(double), rows,
+                       cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy2D(K)");
+    }
+  }
+  std::string keep = g_err;
+  pool_free(fx); pool_free(fy); pool_free(K_dev);
+  qk_batch_destroy(bx); qk_batch_destroy(by);
+  g_err = keep;
+  return rc;
+}
+
+int qk_dmma_peak(int device, int iters, double* tflops) {
+  if (!tflops || iters < 1) return fail(QK_ERR_ARG, "bad arguments");
+  QK_CUDA(cudaSetDevice(device), "cudaSetDevice");
+  QK_CUDA(qk_run_dmma_peak(iters, tflops), "dmma peak kernel");
+  return QK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,429 @@
+// Stage 2: all-pairs MPS overlaps  K[y][x] = |<psi_y|psi_x>|^2  (replaces x_mps.vdot(y_mps),
+// gpu_backend/kernel_state_ansatz.py:380-387, and abs(inner(y,x))^2, KernelPkg/src/KernelPkg.jl:103-109).
+//
+// qk_gram_dmma_kernel -- the product kernel.  One CTA owns a tile of TI kets x TJ bras; one warp
+// per (bra, ket) pair carries the transfer matrix E (bra bond x ket bond, complex, <= 16x16) in
+// FP64 tensor-core accumulator fragments for the whole n-site sweep and never spills it to memory:
+//     T_p^T = A_x[p]^T  * E^T          (step 1; E   is consumed directly as the MMA B operand)
+//     E'   += A_y[p]^dag * T_p          (step 2; T^T is consumed directly as the MMA B operand)
+// using mma.sync.m8n8k4.f64 (DMMA).  The accumulator layout of one MMA is exactly the B-operand
+// layout of the next when the contraction index is taken in the order (even columns, odd columns),
+// so the site tensors are stored in HBM already permuted into A-fragment order ("frag" layout,
+// written by qk_pack_kernel) and arrive in shared memory through a 3-stage cp.async.bulk (TMA)
+// + mbarrier pipeline fed by a dedicated producer warp.
+//
+// qk_gram_store_kernel -- CUDA-core FP64 cross-check on the unpadded stores (any chi); used by
+// tests and as the path for bond dimensions above 16.
+#include <stdint.h>
+#include "qk_kernels.cuh"
+
+#define QK_TI 4
+#define QK_TJ 2
+#define QK_NS 3
+#define QK_GRAM_WARPS (QK_TI * QK_TJ)
+
+void qk_gram_dmma_tile_shape(int* ti, int* tj) { *ti = QK_TI; *tj = QK_TJ; }
+
+void qk_frag_layout(int n, const int32_t* D, FragLayout* L, int64_t* site_off_bytes) {
+  int64_t off = 0;
+  for (int s = 0; s < n; ++s) {
+    if (site_off_bytes) site_off_bytes[s] = off;
+    off += (int64_t)D[s] * D[s + 1] * 32;
+  }
+  if (site_off_bytes) site_off_bytes[n] = off;
+  L->n = n;
+  L->data_bytes = off;
+  L->stride_bytes = off + (((int64_t)(n + 1) + 15) & ~(int64_t)15);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pack: unpadded store -> frag layout
+//   block(s) doubles index d:  e = d&1, lane = (d>>1)&31, h = (d>>6)&1, kt, mt, p from d>>7
+//   value = Re/Im (h) of A[c = 8kt + 2(lane&3) + e][p][c' = 8mt + (lane>>2)]   (0 outside chi)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) qk_pack_kernel(int n, const c128* __restrict__ store, int64_t state_stride,
+                                                      const int64_t* __restrict__ site_off,
+                                                      const int32_t* __restrict__ chi, const int32_t* __restrict__ D,
+                                                      const int64_t* __restrict__ frag_off, int64_t frag_stride,
+                                                      int64_t frag_data, unsigned char* __restrict__ frag) {
+  const int s = blockIdx.x;
+  const int i = blockIdx.y;
+  const int Dl = D[s], Dr = D[s + 1];
+  const int KT = Dl >> 3, MT = Dr >> 3;
+  const int cl = chi[(size_t)i * (n + 1) + s], cr = chi[(size_t)i * (n + 1) + s + 1];
+  const c128* A = store + (size_t)i * state_stride + site_off[s];
+  double* out = (double*)(frag + (size_t)i * frag_stride + frag_off[s]);
+  const int total = Dl * Dr * 4;
+  for (int d = threadIdx.x; d < total; d += blockDim.x) {
+    const int e = d & 1, lane = (d >> 1) & 31, h = (d >> 6) & 1;
+    int rest = d >> 7;
+    const int kt = rest % KT; rest /= KT;
+    const int mt = rest % MT;
+    const int p = rest / MT;
+    const int cidx = 8 * kt + 2 * (lane & 3) + e;
+    const int cp = 8 * mt + (lane >> 2);
+    double v = 0.0;
+    if (cidx < cl && cp < cr) {
+      const c128 a = A[(size_t)(cidx * 2 + p) * cr + cp];
+      v = h ? a.y : a.x;
+    }
+    out[d] = v;
+  }
+  if (s == 0) {
+    unsigned char* tc = frag + (size_t)i * frag_stride + frag_data;
+    for (int b = threadIdx.x; b <= n; b += blockDim.x) tc[b] = (unsigned char)((chi[(size_t)i * (n + 1) + b] + 7) >> 3);
+  }
+}
+
+cudaError_t qk_launch_pack(int n, int N, const c128* store, int64_t state_stride, const int64_t* site_off_dev,
+                           const int32_t* chi_dev, const int32_t* D_dev, const int64_t* frag_off_dev,
+                           int64_t frag_stride_bytes, int64_t frag_data_bytes, void* frag_dev, cudaStream_t stream) {
+  if (N <= 0) return cudaSuccess;
+  dim3 grid(n, N);
+  qk_pack_kernel<<<grid, 256, 0, stream>>>(n, store, state_stride, site_off_dev, chi_dev, D_dev, frag_off_dev,
+                                           frag_stride_bytes, frag_data_bytes, (unsigned char*)frag_dev);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t qk_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void qk_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void qk_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void qk_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void qk_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void qk_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// FP64 tensor-core MMA, D(8x8) += A(8x4) * B(4x8).  Fragments: A: row = lane/4, col = lane%4;
+// B: row = lane%4, col = lane/4; C/D: row = lane/4, cols = 2*(lane%4) + {0,1}.
+__device__ __forceinline__ void qk_dmma(double (&acc)[2], double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(acc[0]), "+d"(acc[1]) : "d"(a), "d"(b));
+}
+
+// ------------------------------------------------------------------------------------------------
+// DMMA Gram kernel.  NT = max 8x8 tiles per bond (1: D <= 8, 2: D <= 16).
+// ------------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__((QK_GRAM_WARPS + 1) * 32, 1) qk_gram_dmma_kernel(const __grid_constant__ GramParams P) {
+  extern __shared__ __align__(128) unsigned char gsm[];
+  const int n = P.n;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int stage_bytes = QK_TI * P.slot_x + QK_TJ * P.slot_y;
+  unsigned char* stage0 = gsm;
+  uint64_t* bars = (uint64_t*)(gsm + (size_t)QK_NS * stage_bytes);   // full[NS], empty[NS]
+  int* sDx = (int*)(bars + 2 * QK_NS);
+  int* sDy = sDx + (n + 1);
+  unsigned char* stc = (unsigned char*)(sDy + (n + 1));              // [(TI+TJ)][n+1]
+
+  const int4 tile = P.tiles[blockIdx.x];
+  const int y0 = tile.x, x0 = tile.y, y_end = tile.z, x_end = tile.w;
+
+  for (int b = threadIdx.x; b <= n; b += blockDim.x) { sDx[b] = P.Dx[b]; sDy[b] = P.Dy[b]; }
+  for (int t = warp; t < QK_TI + QK_TJ; t += QK_GRAM_WARPS + 1) {
+    const bool is_x = t < QK_TI;
+    int idx = is_x ? x0 + t : y0 + (t - QK_TI);
+    const int lim = is_x ? P.Nx : P.Ny;
+    if (idx >= lim) idx = lim - 1;
+    const unsigned char* src = is_x ? P.fragX + (size_t)idx * P.strideX + P.dataX : P.fragY + (size_t)idx * P.strideY + P.dataY;
+    for (int b = lane; b <= n; b += 32) stc[t * (n + 1) + b] = src[b];
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < QK_NS; ++s) {
+      qk_mbar_init(qk_smem_u32(&bars[s]), 1);                       // full: producer's expect_tx arrive
+      qk_mbar_init(qk_smem_u32(&bars[QK_NS + s]), QK_GRAM_WARPS);   // empty: one arrive per consumer warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == QK_GRAM_WARPS) {
+    // ===== producer warp: one lane streams the site blocks of the tile's TI kets and TJ bras =====
+    if (lane == 0) {
+      for (int s = 0; s < n; ++s) {
+        const int st = s % QK_NS;
+        const uint32_t par = (uint32_t)((s / QK_NS) & 1);
+        qk_mbar_wait(qk_smem_u32(&bars[QK_NS + st]), par ^ 1u);
+        const uint32_t bx = (uint32_t)(sDx[s] * sDx[s + 1] * 32);
+        const uint32_t by = (uint32_t)(sDy[s] * sDy[s + 1] * 32);
+        const uint32_t full = qk_smem_u32(&bars[st]);
+        qk_mbar_expect_tx(full, QK_TI * bx + QK_TJ * by);
+        unsigned char* dst = stage0 + (size_t)st * stage_bytes;
+        const int64_t ox = P.offx[s], oy = P.offy[s];
+#pragma unroll
+        for (int t = 0; t < QK_TI; ++t) {
+          int xi = x0 + t; if (xi >= P.Nx) xi = P.Nx - 1;
+          qk_bulk_g2s(qk_smem_u32(dst + (size_t)t * P.slot_x), P.fragX + (size_t)xi * P.strideX + ox, bx, full);
+        }
+#pragma unroll
+        for (int t = 0; t < QK_TJ; ++t) {
+          int yi = y0 + t; if (yi >= P.Ny) yi = P.Ny - 1;
+          qk_bulk_g2s(qk_smem_u32(dst + (size_t)QK_TI * P.slot_x + (size_t)t * P.slot_y),
+                      P.fragY + (size_t)yi * P.strideY + oy, by, full);
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== consumer warps: one (bra y, ket x) pair each =====
+  const int ti = warp % QK_TI, tj = warp / QK_TI;
+  const int x = x0 + ti, y = y0 + tj;
+  const bool active = (x < x_end) && (y < y_end) && (!P.symmetric || x <= y);
+  const unsigned char* tcx = stc + ti * (n + 1);
+  const unsigned char* tcy = stc + (QK_TI + tj) * (n + 1);
+
+  double Er[NT][NT][2], Ei[NT][NT][2];   // E[bra tile][ket tile]
+#pragma unroll
+  for (int a = 0; a < NT; ++a)
+#pragma unroll
+    for (int b = 0; b < NT; ++b) { Er[a][b][0] = Er[a][b][1] = 0.0; Ei[a][b][0] = Ei[a][b][1] = 0.0; }
+  if (lane == 0) Er[0][0][0] = 1.0;   // E_0 = [1]
+
+  for (int s = 0; s < n; ++s) {
+    const int st = s % QK_NS;
+    const uint32_t par = (uint32_t)((s / QK_NS) & 1);
+    qk_mbar_wait(qk_smem_u32(&bars[st]), par);
+    if (active) {
+      const int KTx = sDx[s] >> 3, MTx = sDx[s + 1] >> 3;
+      const int KTy = sDy[s] >> 3, MTy = sDy[s + 1] >> 3;
+      const int kx = tcx[s], mx = tcx[s + 1], ky = tcy[s], my = tcy[s + 1];
+      const unsigned char* sb = stage0 + (size_t)st * stage_bytes;
+      const double2* bx = (const double2*)(sb + (size_t)ti * P.slot_x);
+      const double2* by = (const double2*)(sb + (size_t)QK_TI * P.slot_x + (size_t)tj * P.slot_y);
+      double Fr[NT][NT][2], Fi[NT][NT][2];
+#pragma unroll
+      for (int a = 0; a < NT; ++a)
+#pragma unroll
+        for (int b = 0; b < NT; ++b) { Fr[a][b][0] = Fr[a][b][1] = 0.0; Fi[a][b][0] = Fi[a][b][1] = 0.0; }
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        double Tr[NT][NT][2], Ti[NT][NT][2];   // T^T[ket-right tile][bra-left tile]
+#pragma unroll
+        for (int a = 0; a < NT; ++a)
+#pragma unroll
+          for (int b = 0; b < NT; ++b) { Tr[a][b][0] = Tr[a][b][1] = 0.0; Ti[a][b][0] = Ti[a][b][1] = 0.0; }
+        // step 1: T^T[c'][a] += sum_c A_x[c,p,c'] * E[a][c]
+#pragma unroll
+        for (int mt = 0; mt < NT; ++mt) {
+          if (mt < mx) {
+#pragma unroll
+            for (int kt = 0; kt < NT; ++kt) {
+              if (kt < kx) {
+                const int fi = (((p * MTx + mt) * KTx + kt) * 2) * 32 + lane;
+                const double2 mr = bx[fi], mi = bx[fi + 32];
+                const double n0 = -mi.x, n1 = -mi.y;
+#pragma unroll
+                for (int at = 0; at < NT; ++at) {
+                  if (at < ky) {
+                    qk_dmma(Tr[mt][at], mr.x, Er[at][kt][0]);
+                    qk_dmma(Ti[mt][at], mr.x, Ei[at][kt][0]);
+                    qk_dmma(Tr[mt][at], n0, Ei[at][kt][0]);
+                    qk_dmma(Ti[mt][at], mi.x, Er[at][kt][0]);
+                    qk_dmma(Tr[mt][at], mr.y, Er[at][kt][1]);
+                    qk_dmma(Ti[mt][at], mr.y, Ei[at][kt][1]);
+                    qk_dmma(Tr[mt][at], n1, Ei[at][kt][1]);
+                    qk_dmma(Ti[mt][at], mi.y, Er[at][kt][1]);
+                  }
+                }
+              }
+            }
+          }
+        }
+        // step 2: E'[b'][c'] += sum_a conj(A_y[a,p,b']) * T[a][c']
+#pragma unroll
+        for (int bt = 0; bt < NT; ++bt) {
+          if (bt < my) {
+#pragma unroll
+            for (int at = 0; at < NT; ++at) {
+              if (at < ky) {
+                const int fi = (((p * MTy + bt) * KTy + at) * 2) * 32 + lane;
+                const double2 mr = by[fi], mi = by[fi + 32];
+                const double n0 = -mi.x, n1 = -mi.y;
+#pragma unroll
+                for (int ct = 0; ct < NT; ++ct) {
+                  if (ct < mx) {
+                    qk_dmma(Fr[bt][ct], mr.x, Tr[ct][at][0]);
+                    qk_dmma(Fi[bt][ct], mr.x, Ti[ct][at][0]);
+                    qk_dmma(Fr[bt][ct], mi.x, Ti[ct][at][0]);
+                    qk_dmma(Fi[bt][ct], n0, Tr[ct][at][0]);
+                    qk_dmma(Fr[bt][ct], mr.y, Tr[ct][at][1]);
+                    qk_dmma(Fi[bt][ct], mr.y, Ti[ct][at][1]);
+                    qk_dmma(Fr[bt][ct], mi.y, Ti[ct][at][1]);
+                    qk_dmma(Fi[bt][ct], n1, Tr[ct][at][1]);
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < NT; ++a)
+#pragma unroll
+        for (int b = 0; b < NT; ++b) {
+          Er[a][b][0] = Fr[a][b][0]; Er[a][b][1] = Fr[a][b][1];
+          Ei[a][b][0] = Fi[a][b][0]; Ei[a][b][1] = Fi[a][b][1];
+        }
+    }
+    __syncwarp();
+    if (lane == 0) qk_mbar_arrive(qk_smem_u32(&bars[QK_NS + st]));
+  }
+  if (active && lane == 0) {
+    const double v = Er[0][0][0] * Er[0][0][0] + Ei[0][0][0] * Ei[0][0][0];
+    P.K[(size_t)y * P.ldk + x] = v;
+    if (P.symmetric) P.K[(size_t)x * P.ldk + y] = v;
+  }
+}
+
+static size_t gram_smem_bytes(const GramParams& P) {
+  size_t b = (size_t)QK_NS * (QK_TI * (size_t)P.slot_x + QK_TJ * (size_t)P.slot_y);
+  b += 2 * QK_NS * sizeof(uint64_t);
+  b += 2 * (size_t)(P.n + 1) * sizeof(int);
+  b += (size_t)(QK_TI + QK_TJ) * (P.n + 1);
+  return (b + 127) & ~(size_t)127;
+}
+
+template <int NT>
+static cudaError_t launch_gram_nt(const GramParams& P, cudaStream_t stream) {
+  const size_t smem = gram_smem_bytes(P);
+  cudaError_t e = cudaFuncSetAttribute(qk_gram_dmma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  qk_gram_dmma_kernel<NT><<<P.n_cta_tiles, (QK_GRAM_WARPS + 1) * 32, smem, stream>>>(P);
+  return cudaGetLastError();
+}
+
+cudaError_t qk_launch_gram_dmma(const GramParams& P, int maxD, cudaStream_t stream) {
+  if (P.n_cta_tiles <= 0) return cudaSuccess;
+  if (maxD <= 8) return launch_gram_nt<1>(P, stream);
+  if (maxD <= 16) return launch_gram_nt<2>(P, stream);
+  return cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CUDA-core cross-check kernel: one CTA per (y, x) pair, E and T in shared memory, true dims.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) qk_gram_store_kernel(int n, const c128* __restrict__ storeX, int64_t strideX,
+                                                           const int64_t* __restrict__ offX, const int32_t* __restrict__ chiX,
+                                                           int capx, const c128* __restrict__ storeY, int64_t strideY,
+                                                           const int64_t* __restrict__ offY, const int32_t* __restrict__ chiY,
+                                                           int capy, double* __restrict__ K, int64_t ldk) {
+  extern __shared__ __align__(16) unsigned char ssm[];
+  c128* E = (c128*)ssm;                       // [capy][capx]
+  c128* T = E + (size_t)capy * capx;          // [2*capy][capx]
+  const int x = blockIdx.x, y = blockIdx.y;
+  const c128* Sx = storeX + (size_t)x * strideX;
+  const c128* Sy = storeY + (size_t)y * strideY;
+  const int32_t* cx = chiX + (size_t)x * (n + 1);
+  const int32_t* cy = chiY + (size_t)y * (n + 1);
+  if (threadIdx.x == 0) E[0] = cmake(1.0, 0.0);
+  __syncthreads();
+  for (int s = 0; s < n; ++s) {
+    const int cxl = cx[s], cxr = cx[s + 1], cyl = cy[s], cyr = cy[s + 1];
+    const c128* Ax = Sx + offX[s];
+    const c128* Ay = Sy + offY[s];
+    // T[(a,p), c'] = sum_c E[a,c] Ax[c,p,c']
+    for (int idx = threadIdx.x; idx < cyl * 2 * cxr; idx += blockDim.x) {
+      const int a = idx / (2 * cxr);
+      const int rem = idx - a * 2 * cxr;
+      const int p = rem / cxr, cp = rem - p * cxr;
+      c128 acc = cmake(0, 0);
+      for (int c = 0; c < cxl; ++c) cfma(acc, E[a * cxl + c], Ax[(size_t)(c * 2 + p) * cxr + cp]);
+      T[idx] = acc;
+    }
+    __syncthreads();
+    // E'[b', c'] = sum_{a,p} conj(Ay[a,p,b']) T[(a,p), c']
+    for (int idx = threadIdx.x; idx < cyr * cxr; idx += blockDim.x) {
+      const int bp = idx / cxr, cp = idx - bp * cxr;
+      c128 acc = cmake(0, 0);
+      for (int ap = 0; ap < 2 * cyl; ++ap) cfmac(acc, Ay[(size_t)ap * cyr + bp], T[ap * cxr + cp]);
+      E[idx] = acc;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) K[(size_t)y * ldk + x] = E[0].x * E[0].x + E[0].y * E[0].y;
+}
+
+cudaError_t qk_launch_gram_store(int n, const c128* storeX, int64_t strideX, const int64_t* site_off_x,
+                                 const int32_t* chiX, int capx, int Nx, const c128* storeY, int64_t strideY,
+                                 const int64_t* site_off_y, const int32_t* chiY, int capy, int Ny, double* K,
+                                 int64_t ldk, cudaStream_t stream) {
+  if (Nx <= 0 || Ny <= 0) return cudaSuccess;
+  const size_t smem = (size_t)3 * capx * capy * sizeof(c128);
+  cudaError_t e = cudaFuncSetAttribute(qk_gram_store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid(Nx, Ny);
+  qk_gram_store_kernel<<<grid, 64, smem, stream>>>(n, storeX, strideX, site_off_x, chiX, capx, storeY, strideY,
+                                                   site_off_y, chiY, capy, K, ldk);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// DMMA peak microbenchmark (roofline denominator for stage 2; MEASURED_PEAKS.json has no FP64 figure)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) qk_dmma_peak_kernel(int iters, double* sink) {
+  double acc[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+  const double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qk_dmma(acc[i], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += acc[i][0] + acc[i][1];
+  if (s == 123.456) sink[0] = s;
+}
+
+cudaError_t qk_run_dmma_peak(int iters, double* tflops) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  double* sink = nullptr;
+  cudaError_t e = cudaMalloc(&sink, sizeof(double));
+  if (e != cudaSuccess) return e;
+  const int grid = sms * 4, block = 256;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  qk_dmma_peak_kernel<<<grid, block>>>(iters / 8 + 1, sink);   // warm-up
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0);
+    qk_dmma_peak_kernel<<<grid, block>>>(iters, sink);
+    cudaEventRecord(e1);
+    e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) break;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(sink);
+  if (e != cudaSuccess) return e;
+  const double flops = (double)grid * (block / 32) * (double)iters * 8.0 * 512.0;
+  *tflops = flops / (best * 1e-3) / 1e12;
+  return cudaGetLastError();
+}

@@ -1,0 +1,56 @@
+// Launch interfaces of the device kernels (implemented in qk_sim.cu / qk_gram.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "qk_types.h"
+
+// ---- stage 1 ----
+// Launches the persistent simulation kernel for group size G in {32, 64, 128, 256}.
+cudaError_t qk_launch_sim(const SimParams& P, int G, size_t smem_bytes, int* work_counter, cudaStream_t stream,
+                          int* grid_out);
+
+// ---- exchange format ("frag") ----
+// Per state: for every site s a block of Dl*Dr*4 doubles in DMMA A-fragment order, then n+1 bytes
+// (padded to 16) holding ceil(chi_b / 8) per bond.  See DESIGN.md "Data layout".
+struct FragLayout {
+  int n;
+  int64_t data_bytes;      // bytes of fragment data per state
+  int64_t stride_bytes;    // data_bytes + align16(n+1)
+};
+void qk_frag_layout(int n, const int32_t* D, FragLayout* L, int64_t* site_off_bytes /*[n+1]*/);
+
+cudaError_t qk_launch_pack(int n, int N, const c128* store, int64_t state_stride, const int64_t* site_off_dev,
+                           const int32_t* chi_dev, const int32_t* D_dev, const int64_t* frag_off_dev,
+                           int64_t frag_stride_bytes, int64_t frag_data_bytes, void* frag_dev, cudaStream_t stream);
+
+// ---- stage 2 ----
+struct GramParams {
+  int n;
+  const int32_t* Dx;        // device [n+1]
+  const int32_t* Dy;        // device [n+1]
+  const int64_t* offx;      // device [n+1] byte offsets of the site blocks
+  const int64_t* offy;
+  const unsigned char* fragX;
+  const unsigned char* fragY;
+  int64_t strideX, strideY; // bytes per state
+  int64_t dataX, dataY;     // bytes of fragment data per state (tile-count bytes follow)
+  int Nx, Ny;
+  const int4* tiles;        // device [n_cta_tiles]: (y0, x0, y_end, x_end)
+  int n_cta_tiles;
+  int symmetric;
+  double* K;
+  int64_t ldk;
+  int slot_x, slot_y;       // bytes reserved per state per pipeline stage
+};
+// DMMA + bulk-copy pipeline kernel; requires max(D) <= 16.
+cudaError_t qk_launch_gram_dmma(const GramParams& P, int maxD, cudaStream_t stream);
+void qk_gram_dmma_tile_shape(int* ti, int* tj);
+
+// CUDA-core cross-check on the unpadded stores
+cudaError_t qk_launch_gram_store(int n, const c128* storeX, int64_t strideX, const int64_t* site_off_x,
+                                 const int32_t* chiX, int capx, int Nx,
+                                 const c128* storeY, int64_t strideY, const int64_t* site_off_y,
+                                 const int32_t* chiY, int capy, int Ny,
+                                 double* K, int64_t ldk, cudaStream_t stream);
+
+cudaError_t qk_run_dmma_peak(int iters, double* tflops);

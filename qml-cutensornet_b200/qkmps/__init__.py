@@ -1,0 +1,308 @@
+"""ctypes binding of libqkmps.so (C ABI: include/qkmps.h) -- the B200 quantum-kernel MPS engine.
+
+There is no CPU fallback: importing works anywhere (so CPU-only tests can check the ABI), but every
+compute call needs the CUDA library and an sm_100 device and raises ``QkError`` otherwise.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import pathlib
+import subprocess
+
+import numpy as np
+
+_HERE = pathlib.Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libqkmps.so"
+CSRC = _HERE.parent / "csrc"
+
+QK_TRUNC_ITENSORS = 0
+QK_TRUNC_PYTKET = 1
+QK_FLAG_CAP_HIT = 1
+QK_FLAG_NO_CONVERGE = 2
+QK_ERR_LIMIT = -3
+CHI_LIMIT = 32          # shared-memory-resident stage-1 kernel
+DMMA_D_LIMIT = 16       # register-resident tensor-core overlap kernel
+
+GATE_KIND = {"H": 0, "Rz": 1, "Rx": 2, "XXPhase": 3, "ZZPhase": 4, "SWAP": 5}
+
+
+class QkError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libqkmps error {code}: {msg}")
+        self.code = code
+
+
+class QkGate(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("q0", ctypes.c_int32), ("q1", ctypes.c_int32),
+                ("fa", ctypes.c_int32), ("fb", ctypes.c_int32), ("coeff", ctypes.c_double)]
+
+
+class QkPlanInfo(ctypes.Structure):
+    _fields_ = [("n_qubits", ctypes.c_int32), ("n_gates", ctypes.c_int32), ("n_ops", ctypes.c_int32),
+                ("n_ops_2q", ctypes.c_int32), ("n_ops_1q", ctypes.c_int32), ("n_moves", ctypes.c_int32),
+                ("chi_cap", ctypes.c_int32), ("threads", ctypes.c_int32), ("trunc_mode", ctypes.c_int32),
+                ("smem_bytes", ctypes.c_int32), ("state_stride", ctypes.c_int64), ("trunc_error", ctypes.c_double)]
+
+
+class QkOpView(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("site", ctypes.c_int32), ("fa", ctypes.c_int32),
+                ("fb", ctypes.c_int32), ("dir", ctypes.c_int32), ("coeff", ctypes.c_double)]
+
+
+EXPORTS = [
+    "qk_version", "qk_last_error", "qk_device_count",
+    "qk_plan_create_gates", "qk_plan_create_ansatz", "qk_plan_info", "qk_plan_ops", "qk_plan_destroy",
+    "qk_simulate", "qk_simulate_dev", "qk_batch_sim_ms", "qk_batch_size", "qk_batch_info", "qk_batch_export",
+    "qk_batch_import", "qk_batch_max_chi", "qk_batch_destroy", "qk_frag_stride", "qk_batch_pack",
+    "qk_gram_frags", "qk_gram_store", "qk_gram_host", "qk_dmma_peak",
+]
+
+_lib = None
+
+
+def build(force: bool = False) -> pathlib.Path:
+    """Compile libqkmps.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    srcs = [CSRC / f for f in ("qk_api.cu", "qk_sim.cu", "qk_gram.cu", "qk_plan.cpp", "qk_types.h",
+                               "qk_sim_core.h", "qk_plan.h", "qk_kernels.cuh")]
+    srcs.append(_HERE.parent.parent / "include" / "qkmps.h")
+    stale = force or not LIB_PATH.exists() or any(s.stat().st_mtime > LIB_PATH.stat().st_mtime for s in srcs)
+    if stale:
+        subprocess.check_call(["make", "-C", str(CSRC)], stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    """Load libqkmps.so; fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise QkError(-2, f"{LIB_PATH} is missing: build it with `make -C {CSRC}` "
+                          "(there is no CPU fallback for the quantum-kernel path)")
+    L = ctypes.CDLL(str(LIB_PATH))
+    L.qk_last_error.restype = ctypes.c_char_p
+    L.qk_version.restype = ctypes.c_int
+    for name in EXPORTS:
+        getattr(L, name)  # AttributeError if the symbol is not exported
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc < 0:
+        raise QkError(rc, lib().qk_last_error().decode())
+    return rc
+
+
+def _p(arr, ctype):
+    return arr.ctypes.data_as(ctypes.POINTER(ctype))
+
+
+def gates_to_c(gates):
+    """[(name, qubits, param)] with param None | ("lin", i, c) | ("prod", a, b, c) | ("const", alpha)."""
+    arr = (QkGate * max(len(gates), 1))()
+    for i, (name, qubits, param) in enumerate(gates):
+        if name not in GATE_KIND:
+            raise RuntimeError(f"Unrecognised {name}.")
+        g = arr[i]
+        g.kind = GATE_KIND[name]
+        g.q0 = int(qubits[0])
+        g.q1 = int(qubits[1]) if len(qubits) > 1 else -1
+        g.fa, g.fb, g.coeff = -1, -1, 0.0
+        if param is not None:
+            if param[0] == "lin":
+                g.fa, g.coeff = int(param[1]), float(param[2])
+            elif param[0] == "prod":
+                g.fa, g.fb, g.coeff = int(param[1]), int(param[2]), float(param[3])
+            elif param[0] == "const":
+                g.coeff = float(param[1])
+            else:
+                raise RuntimeError(f"bad gate parameter {param!r}")
+    return arr
+
+
+class Plan:
+    """Compiled static op schedule of one ansatz (qk_plan)."""
+
+    def __init__(self, n_qubits, gates, trunc_mode, trunc_error, chi_cap):
+        self._h = ctypes.c_void_p()
+        carr = gates_to_c(gates)
+        _check(lib().qk_plan_create_gates(int(n_qubits), carr, len(gates), int(trunc_mode),
+                                          ctypes.c_double(trunc_error), int(chi_cap), ctypes.byref(self._h)))
+        self.n_qubits = int(n_qubits)
+        self.chi_cap = int(chi_cap)
+
+    @classmethod
+    def from_ansatz(cls, n_qubits, reps, gamma, pairs, hadamard_init, trunc_mode, trunc_error, chi_cap):
+        self = cls.__new__(cls)
+        self._h = ctypes.c_void_p()
+        pr = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
+        _check(lib().qk_plan_create_ansatz(int(n_qubits), int(reps), ctypes.c_double(gamma), int(bool(hadamard_init)),
+                                           _p(pr, ctypes.c_int32), int(pr.shape[0]), int(trunc_mode),
+                                           ctypes.c_double(trunc_error), int(chi_cap), ctypes.byref(self._h)))
+        self.n_qubits = int(n_qubits)
+        self.chi_cap = int(chi_cap)
+        return self
+
+    def info(self) -> QkPlanInfo:
+        out = QkPlanInfo()
+        _check(lib().qk_plan_info(self._h, ctypes.byref(out)))
+        return out
+
+    def ops(self):
+        n = self.info().n_ops
+        arr = (QkOpView * max(n, 1))()
+        k = _check(lib().qk_plan_ops(self._h, arr, n))
+        return [(o.kind, o.site, o.fa, o.fb, o.dir, o.coeff) for o in arr[:k]]
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.qk_plan_destroy(self._h)
+            self._h = None
+
+
+class Batch:
+    """Device-resident batch of simulated MPS (qk_batch)."""
+
+    def __init__(self, handle):
+        self._h = handle
+        n_states, nq = ctypes.c_int(), ctypes.c_int()
+        _check(lib().qk_batch_size(self._h, ctypes.byref(n_states), ctypes.byref(nq)))
+        self.N, self.n_qubits = n_states.value, nq.value
+
+    def info(self):
+        N, n = self.N, self.n_qubits
+        chi = np.ones((N, n + 1), dtype=np.int32)
+        fid = np.ones(N)
+        tw = np.zeros(N)
+        nbytes = np.zeros(N, dtype=np.int64)
+        flags = np.zeros(N, dtype=np.int32)
+        sweeps = np.zeros(N, dtype=np.int32)
+        _check(lib().qk_batch_info(self._h, _p(chi, ctypes.c_int32), _p(fid, ctypes.c_double), _p(tw, ctypes.c_double),
+                                   _p(nbytes, ctypes.c_int64), _p(flags, ctypes.c_int32), _p(sweeps, ctypes.c_int32)))
+        return dict(chi=chi, fidelity=fid, trunc_weight=tw, nbytes=nbytes, flags=flags, sweeps=sweeps)
+
+    def sim_ms(self) -> float:
+        ms = ctypes.c_float()
+        _check(lib().qk_batch_sim_ms(self._h, ctypes.byref(ms)))
+        return ms.value
+
+    def max_chi(self) -> np.ndarray:
+        out = np.ones(self.n_qubits + 1, dtype=np.int32)
+        _check(lib().qk_batch_max_chi(self._h, _p(out, ctypes.c_int32)))
+        return out
+
+    def export(self, i: int, chi_row=None):
+        """Site tensors of state i as a list of [chi_l, 2, chi_r] complex128 arrays."""
+        if chi_row is None:
+            chi_row = self.info()["chi"][i]
+        total = int(sum(int(chi_row[s]) * 2 * int(chi_row[s + 1]) for s in range(self.n_qubits)))
+        buf = np.zeros(total, dtype=np.complex128)
+        _check(lib().qk_batch_export(self._h, int(i), buf.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(buf.nbytes)))
+        out, o = [], 0
+        for s in range(self.n_qubits):
+            cl, cr = int(chi_row[s]), int(chi_row[s + 1])
+            out.append(buf[o:o + cl * 2 * cr].reshape(cl, 2, cr))
+            o += cl * 2 * cr
+        return out
+
+    def pack(self, D, frag_ptr: int, stream: int = 0):
+        D = np.ascontiguousarray(D, dtype=np.int32)
+        _check(lib().qk_batch_pack(self._h, _p(D, ctypes.c_int32), ctypes.c_void_p(frag_ptr), ctypes.c_void_p(stream)))
+
+    def gram_store(self, other=None) -> tuple[np.ndarray, float]:
+        """CUDA-core cross-check kernel: K[y, x] with y over ``other`` (or self)."""
+        rows = self.N if other is None else other.N
+        K = np.zeros((rows, self.N))
+        ms = ctypes.c_float()
+        _check(lib().qk_gram_store(self._h, None if other is None else other._h, _p(K, ctypes.c_double),
+                                   ctypes.c_int64(self.N), ctypes.byref(ms)))
+        return K, ms.value
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.qk_batch_destroy(self._h)
+            self._h = None
+
+
+def device_count() -> int:
+    c = ctypes.c_int()
+    _check(lib().qk_device_count(ctypes.byref(c)))
+    return c.value
+
+
+def simulate(plan: Plan, X: np.ndarray, device: int = 0) -> Batch:
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    h = ctypes.c_void_p()
+    _check(lib().qk_simulate(plan._h, int(device), _p(X, ctypes.c_double), int(X.shape[0]), int(X.shape[1]),
+                             ctypes.byref(h)))
+    return Batch(h)
+
+
+def simulate_dev(plan: Plan, x_ptr: int, N: int, ldx: int, device: int = 0, stream: int = 0) -> Batch:
+    h = ctypes.c_void_p()
+    _check(lib().qk_simulate_dev(plan._h, int(device), ctypes.c_void_p(stream), ctypes.c_void_p(x_ptr), int(N), int(ldx),
+                                 ctypes.byref(h)))
+    return Batch(h)
+
+
+def import_batch(states, device: int = 0) -> Batch:
+    """Upload MPS made elsewhere: ``states`` = list of lists of [chi_l, 2, chi_r] arrays (test hook)."""
+    N, n = len(states), len(states[0])
+    chi = np.ones((N, n + 1), dtype=np.int32)
+    chunks = []
+    for i, ts in enumerate(states):
+        for s, t in enumerate(ts):
+            chi[i, s], chi[i, s + 1] = t.shape[0], t.shape[2]
+            chunks.append(np.ascontiguousarray(t, dtype=np.complex128).reshape(-1))
+    buf = np.concatenate(chunks)
+    h = ctypes.c_void_p()
+    _check(lib().qk_batch_import(int(device), n, N, _p(chi, ctypes.c_int32), buf.ctypes.data_as(ctypes.c_void_p),
+                                 ctypes.c_int64(buf.nbytes), ctypes.byref(h)))
+    return Batch(h)
+
+
+def pad_dims(max_chi) -> np.ndarray:
+    return ((np.asarray(max_chi, dtype=np.int64) + 7) // 8 * 8).astype(np.int32)
+
+
+def frag_stride(n_qubits: int, D) -> int:
+    D = np.ascontiguousarray(D, dtype=np.int32)
+    out = ctypes.c_int64()
+    _check(lib().qk_frag_stride(int(n_qubits), _p(D, ctypes.c_int32), ctypes.byref(out)))
+    return out.value
+
+
+def gram_frags(device, n_qubits, Dx, fragx_ptr, Nx, Dy, fragy_ptr, Ny, tiles, symmetric, k_ptr, ldk, stream=0) -> float:
+    Dx = np.ascontiguousarray(Dx, dtype=np.int32)
+    Dy = Dx if Dy is None else np.ascontiguousarray(Dy, dtype=np.int32)
+    tiles = np.ascontiguousarray(np.asarray(tiles, dtype=np.int32).reshape(-1, 4))
+    ms = ctypes.c_float()
+    _check(lib().qk_gram_frags(int(device), ctypes.c_void_p(stream), int(n_qubits), _p(Dx, ctypes.c_int32),
+                               ctypes.c_void_p(fragx_ptr), int(Nx), _p(Dy, ctypes.c_int32),
+                               ctypes.c_void_p(fragy_ptr or 0), int(Ny), _p(tiles, ctypes.c_int32),
+                               int(tiles.shape[0]), int(bool(symmetric)), ctypes.c_void_p(k_ptr), ctypes.c_int64(ldk),
+                               ctypes.byref(ms)))
+    return ms.value
+
+
+def gram_host(plan: Plan, X, Y=None, device: int = 0) -> np.ndarray:
+    """Whole path through the C ABI with host buffers (qk_gram_host)."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    rows = X.shape[0]
+    yp, ny = None, 0
+    if Y is not None:
+        Y = np.ascontiguousarray(Y, dtype=np.float64)
+        rows, ny, yp = Y.shape[0], Y.shape[0], _p(Y, ctypes.c_double)
+    K = np.zeros((rows, X.shape[0]))
+    _check(lib().qk_gram_host(plan._h, int(device), _p(X, ctypes.c_double), int(X.shape[0]), yp, int(ny),
+                              int(X.shape[1]), _p(K, ctypes.c_double), ctypes.c_int64(X.shape[0])))
+    return K
+
+
+def dmma_peak(device: int = 0, iters: int = 20000) -> float:
+    out = ctypes.c_double()
+    _check(lib().qk_dmma_peak(int(device), int(iters), ctypes.byref(out)))
+    return out.value

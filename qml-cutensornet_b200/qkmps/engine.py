@@ -1,0 +1,194 @@
+"""Host orchestration of the quantum-kernel path on B200s: shard -> simulate -> exchange -> Gram tiles.
+
+One process per GPU.  ``comm`` is duck-typed like the reference's ``mpi_comm`` (Get_rank / Get_size);
+with more than one rank it must be a ``qkmps.comm.TorchComm`` (torch.distributed: NCCL on GPUs,
+gloo for the CPU-side tests of this logic).  PyTorch is used for device buffers, streams and the
+collectives only; all arithmetic is in libqkmps.so.
+
+Replaces gpu_backend/kernel_state_ansatz.py:152-428 of the reference:
+  * chunking of X over ranks (gpu:154,169-174)            -> ``shard_bounds``
+  * per-chunk simulate loop (gpu:213-231,255-273)          -> one stage-1 kernel launch per shard
+  * pickled-MPS round robin (gpu:342-352,416-419)          -> one all-gather of the packed "frag" buffers
+  * per-pair vdot loop + symmetric fill (gpu:366-405)      -> stage-2 kernel over this rank's row blocks
+  * dense reduce(SUM) to root (gpu:428)                    -> reduce of the (disjointly filled) K buffers
+"""
+
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from . import (CHI_LIMIT, DMMA_D_LIMIT, QK_FLAG_CAP_HIT, QK_FLAG_NO_CONVERGE, Batch, Plan, QkError, frag_stride,
+               gram_frags, pad_dims, simulate_dev)
+
+ROW_BLOCK = 8   # Gram rows are dealt to ranks in blocks of this many rows (multiple of the kernel's TJ)
+
+
+def shard_bounds(n_items: int, n_ranks: int, rank: int) -> tuple[int, int]:
+    """Contiguous chunk of ceil(N / n_ranks) items per rank (reference gpu:154,169-174)."""
+    per = -(-n_items // n_ranks) if n_items > 0 else 0
+    lo = min(rank * per, n_items)
+    return lo, min(lo + per, n_items)
+
+
+def row_tiles(n_rows: int, n_cols: int, symmetric: bool, n_ranks: int, rank: int, row_block: int = ROW_BLOCK):
+    """Row blocks owned by ``rank`` as [r0, r1, c0, c1] tiles.
+
+    Symmetric (train) Gram: only x <= y is computed, so row block b costs ~ (b+1) units; blocks are
+    dealt in a boustrophedon (0..R-1, R-1..0, ...) order, which balances the triangle to within one
+    block per rank.  Rectangular Gram: plain cyclic deal.
+    """
+    tiles = []
+    n_blocks = -(-n_rows // row_block)
+    for b in range(n_blocks):
+        rnd, pos = divmod(b, n_ranks)
+        owner = pos if (rnd % 2 == 0 or not symmetric) else n_ranks - 1 - pos
+        if owner != rank:
+            continue
+        r0, r1 = b * row_block, min((b + 1) * row_block, n_rows)
+        tiles.append([r0, r1, 0, min(r1, n_cols) if symmetric else n_cols])
+    return tiles
+
+
+class SingleComm:
+    """Stand-in for ``MPI.COMM_WORLD`` when one process drives one GPU (mpi4py is optional)."""
+
+    def Get_rank(self):
+        return 0
+
+    def Get_size(self):
+        return 1
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise QkError(-2, "no CUDA device: the quantum-kernel path has no CPU fallback")
+    return torch
+
+
+def _simulate_shard(plan_factory, X_shard, device, chi_cap, comm, n_qubits):
+    """Stage 1 on this rank's shard; doubles the bond cap (on every rank) while any state hit it.
+
+    ``X_shard`` is a host numpy array (copied through pinned memory) or a CUDA float64 tensor.
+    """
+    torch = _torch()
+    from .comm import allreduce_max_int
+    if isinstance(X_shard, torch.Tensor):
+        xt = X_shard.contiguous()
+    elif len(X_shard):
+        xt = torch.from_numpy(np.ascontiguousarray(X_shard, dtype=np.float64)).pin_memory().to(
+            f"cuda:{device}", non_blocking=True)
+    else:
+        xt = torch.empty((0, n_qubits), device=f"cuda:{device}", dtype=torch.float64)
+    torch.cuda.current_stream().synchronize()
+    launches = 0
+    while True:
+        plan = plan_factory(chi_cap)
+        stream = torch.cuda.current_stream().cuda_stream
+        batch = simulate_dev(plan, xt.data_ptr(), int(xt.shape[0]), int(xt.shape[1]), device=device, stream=stream)
+        launches += 1 if xt.shape[0] else 0
+        info = batch.info()
+        hit = int(np.any(info["flags"] & QK_FLAG_CAP_HIT)) if batch.N else 0
+        hit = allreduce_max_int(comm, hit)
+        if not hit:
+            return plan, batch, info, chi_cap, launches
+        if chi_cap >= CHI_LIMIT:
+            raise QkError(-3, f"bond dimension exceeds the shared-memory-resident limit (chi <= {CHI_LIMIT}); "
+                              "the large-chi stage-1 path is not implemented")
+        chi_cap = min(2 * chi_cap, CHI_LIMIT)
+
+
+def build_gram(comm, plan_factory, n_qubits, X, Y=None, chi_cap=16, device=None, return_device=False):
+    """Full path.  Returns (K on rank 0 / None elsewhere, profile dict).
+
+    ``X`` / ``Y``: host numpy arrays, or CUDA float64 tensors already resident in HBM (every rank
+    holds the full arrays, as in the reference).  ``return_device`` leaves K on the GPU (rank 0).
+    """
+    torch = _torch()
+    from .comm import allgather_bytes, allreduce_max_array, reduce_sum_to_root
+    rank, size = comm.Get_rank(), comm.Get_size()
+    if device is None:
+        device = rank % torch.cuda.device_count()   # reference gpu:152
+    torch.cuda.set_device(device)
+    dev = f"cuda:{device}"
+    if not isinstance(X, torch.Tensor):
+        X = np.asarray(X, dtype=np.float64)
+    symmetric = Y is None
+    Nx = len(X)
+    Ny = Nx if symmetric else len(Y)
+    prof = {}
+    t_all = time.perf_counter()
+    launches = 0
+
+    # ---- stage 1 on this rank's shard(s)
+    lo, hi = shard_bounds(Nx, size, rank)
+    plan, bx, info_x, chi_cap, nl = _simulate_shard(plan_factory, X[lo:hi], device, chi_cap, comm, n_qubits)
+    launches += nl
+    by, info_y = None, None
+    if not symmetric:
+        if not isinstance(Y, torch.Tensor):
+            Y = np.asarray(Y, dtype=np.float64)
+        ylo, yhi = shard_bounds(Ny, size, rank)
+        plan, by, info_y, chi_cap2, nl = _simulate_shard(plan_factory, Y[ylo:yhi], device, chi_cap, comm, n_qubits)
+        launches += nl
+        if chi_cap2 != chi_cap:   # Y needed a larger cap: redo X with it so both use one plan
+            chi_cap = chi_cap2
+            plan, bx, info_x, chi_cap, nl = _simulate_shard(plan_factory, X[lo:hi], device, chi_cap, comm, n_qubits)
+            launches += nl
+    prof["sim_ms_x"] = bx.sim_ms()
+    prof["sim_ms_y"] = by.sim_ms() if by is not None else 0.0
+    prof["chi_cap"] = chi_cap
+    prof["info_x"], prof["info_y"] = info_x, info_y
+    prof["plan"] = plan.info()
+    prof["shard"] = (lo, hi)
+
+    # ---- exchange: batch-uniform padded dims, pack, all-gather
+    t0 = time.perf_counter()
+    Dx = pad_dims(allreduce_max_array(comm, bx.max_chi()))
+    Dy = Dx if symmetric else pad_dims(allreduce_max_array(comm, by.max_chi()))
+    if int(max(Dx.max(), Dy.max())) > DMMA_D_LIMIT:
+        raise QkError(-3, f"padded bond dimension {int(max(Dx.max(), Dy.max()))} above the tensor-core overlap "
+                          f"kernel's limit ({DMMA_D_LIMIT}); use Batch.gram_store for such states")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def packed(batch, D, n_total):
+        nonlocal launches
+        stride = frag_stride(n_qubits, D)
+        per = -(-n_total // size)
+        local = torch.empty(max(per, 1) * stride, dtype=torch.uint8, device=dev)
+        if batch.N:
+            batch.pack(D, local.data_ptr(), stream)
+            launches += 1
+        if size == 1:
+            return local, stride
+        return allgather_bytes(comm, local), stride
+
+    fx, stride_x = packed(bx, Dx, Nx)
+    fy, stride_y = (fx, stride_x) if symmetric else packed(by, Dy, Ny)
+    torch.cuda.synchronize()
+    prof["exchange_s"] = time.perf_counter() - t0
+    prof["frag_bytes_per_state"] = (stride_x, stride_y)
+
+    # ---- stage 2 on this rank's row blocks
+    K = torch.zeros((Ny, Nx), dtype=torch.float64, device=dev)
+    tiles = row_tiles(Ny, Nx, symmetric, size, rank)
+    ms = 0.0
+    if tiles:
+        ms = gram_frags(device, n_qubits, Dx, fx.data_ptr(), Nx, None if symmetric else Dy,
+                        None if symmetric else fy.data_ptr(), Ny, tiles, symmetric, K.data_ptr(), Nx, stream)
+        launches += 1
+    prof["gram_ms"] = ms
+    prof["Dx"], prof["Dy"] = Dx, Dy
+    prof["launches"] = launches
+    if size > 1:
+        K = reduce_sum_to_root(comm, K)
+    out = None
+    if rank == 0:
+        out = K if return_device else K.cpu().numpy()
+    torch.cuda.synchronize()
+    prof["total_s"] = time.perf_counter() - t_all
+    bad = int(np.any(info_x["flags"] & QK_FLAG_NO_CONVERGE)) if bx.N else 0
+    prof["no_converge"] = bad
+    return out, prof
