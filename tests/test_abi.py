@@ -1,0 +1,141 @@
+"""CPU tests of the C ABI surface: libqkmps.so loads, exports every symbol include/qkmps.h declares,
+the schedule compiler (host code) behaves, and compute entry points fail loudly without a GPU."""
+import pathlib
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+
+
+def _declared_functions():
+    text = (ROOT / "include" / "qkmps.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(qk_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(qk):
+    import ctypes
+    L = ctypes.CDLL(str(qk.LIB_PATH))
+    names = _declared_functions()
+    assert len(names) >= 20
+    for nm in names:
+        assert hasattr(L, nm), f"{nm} declared in include/qkmps.h but not exported"
+    assert sorted(qk.EXPORTS) == names
+    assert L.qk_version() == 100
+
+
+def test_struct_layouts_match_header(qk):
+    import ctypes
+    assert ctypes.sizeof(qk.QkGate) == 32
+    assert ctypes.sizeof(qk.QkOpView) == 32
+    assert ctypes.sizeof(qk.QkPlanInfo) == 56
+
+
+def _plan(qk, n, r, g, d, cap=16, mode=0):
+    gates = oracle.ansatz_gate_list(n, r, g, oracle.entanglement_graph(n, d))
+    return qk.Plan(n, gates, mode, 1e-16, cap), gates
+
+
+@pytest.mark.parametrize("n,r,d,n2q", [(10, 2, 1, 18), (50, 2, 2, 386), (100, 2, 2, 786), (165, 4, 4, 10360)])
+def test_plan_counts_and_schedule_invariants(qk, n, r, d, n2q):
+    plan, gates = _plan(qk, n, r, 0.5, d)
+    info = plan.info()
+    assert info.n_qubits == n and info.n_gates == len(gates)
+    assert info.n_ops_2q == n2q
+    assert info.n_ops_1q == n * (r + 1)
+    assert info.n_ops == info.n_ops_2q + info.n_ops_1q + info.n_moves
+    # replay the schedule: the orthogonality centre must sit on one of the two sites of every 2-site op
+    centre = None
+    two_q = []
+    for kind, site, fa, fb, direction, coeff in plan.ops():
+        if kind in (3, 4, 5):
+            assert centre is None or centre in (site, site + 1), "centre not adjacent to the gate"
+            centre = site if direction == 1 else site + 1
+            two_q.append((kind, site, fa, fb))
+        elif kind == 16:
+            assert centre == site
+            centre = site + 1
+        elif kind == 17:
+            assert centre == site
+            centre = site - 1
+        else:
+            assert kind in (0, 1, 2)
+    # the 2-qubit ops are the circuit's, in the circuit's order
+    ref = [(qk.GATE_KIND[nm], q[0]) for nm, q, _ in gates if len(q) == 2]
+    assert [(k, s) for k, s, _, _ in two_q] == ref
+
+
+def test_plan_from_ansatz_equals_plan_from_gates(qk):
+    n, r, g, d = 20, 2, 0.7, 3
+    emap = oracle.entanglement_graph(n, d)
+    p1 = qk.Plan.from_ansatz(n, r, g, emap, True, 1, 1e-16, 16)
+    p2, _ = _plan(qk, n, r, g, d, mode=1)
+    o1, o2 = p1.ops(), p2.ops()
+    assert len(o1) == len(o2)
+    for a, b in zip(o1, o2):
+        assert a[:5] == b[:5] and abs(a[5] - b[5]) < 1e-15
+
+
+def test_plan_errors(qk):
+    with pytest.raises(qk.QkError) as e:
+        qk.Plan(4, [("XXPhase", (0, 2), ("const", 0.1))], 0, 1e-16, 4)     # not adjacent
+    assert e.value.code == -1
+    with pytest.raises(RuntimeError):
+        qk.Plan(4, [("CX", (0, 1), None)], 0, 1e-16, 4)                     # unknown gate (cpu:129)
+    with pytest.raises(qk.QkError) as e:
+        qk.Plan(4, [("H", (0,), None)], 0, 1e-16, 64)                       # above the smem-resident limit
+    assert e.value.code == qk.QK_ERR_LIMIT
+    with pytest.raises(qk.QkError):
+        qk.Plan(4, [("Rz", (0,), ("lin", 9, 1.0))], 0, 1e-16, 4)            # feature index out of range
+    with pytest.raises(qk.QkError):
+        qk.Plan(4, [("H", (0,), None)], 0, 1.5, 4)                          # truncation error out of range
+
+
+def test_frag_stride(qk):
+    n = 6
+    D = np.array([8, 8, 16, 16, 16, 8, 8], dtype=np.int32)
+    expect = sum(int(D[s]) * int(D[s + 1]) * 32 for s in range(n)) + 16
+    assert qk.frag_stride(n, D) == expect
+    with pytest.raises(qk.QkError):
+        qk.frag_stride(n, np.array([8, 8, 12, 16, 16, 8, 8], dtype=np.int32))
+    assert list(qk.pad_dims([1, 2, 8, 9, 16, 17])) == [8, 8, 8, 16, 16, 24]
+
+
+def test_compute_fails_loudly_without_gpu(qk):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    plan, _ = _plan(qk, 6, 1, 0.5, 1, cap=4)
+    with pytest.raises(qk.QkError):
+        qk.simulate(plan, oracle.synthetic_features(2, 6, 0))
+    from gpu_backend.kernel_state_ansatz import KernelStateAnsatz, build_kernel_matrix
+    from qkmps.engine import SingleComm
+    ans = KernelStateAnsatz(6, 1, 0.5, [(0, 1)])
+    with pytest.raises(qk.QkError):
+        build_kernel_matrix(SingleComm(), ans, oracle.synthetic_features(2, 6, 0), truncation_error=1e-16)
+
+
+def test_ansatz_mirror_matches_oracle_and_reference_errors():
+    from cpu_backend.kernel_state_ansatz import KernelStateAnsatz as CpuAnsatz
+    from gpu_backend.kernel_state_ansatz import KernelStateAnsatz as GpuAnsatz
+    from qkmps.ansatz import structural_chi_bound
+    from qkmps.synth import entanglement_graph, synthetic_features
+    for n, r, d in [(10, 2, 1), (50, 2, 2), (34, 1, 3)]:
+        emap = oracle.entanglement_graph(n, d)
+        assert entanglement_graph(n, d) == emap
+        a = GpuAnsatz(n, r, 0.5, emap)
+        assert a.ansatz_circ.n_qubits == n and len(a.feature_symbol_list) == n
+        ref = oracle.ansatz_gate_list(n, r, 0.5, emap)
+        assert [(g[0], tuple(g[1]), g[2]) for g in a.ansatz_circ.get_commands()] == [(g[0], tuple(g[1]), g[2]) for g in ref]
+    assert np.array_equal(synthetic_features(5, 7, 3), oracle.synthetic_features(5, 7, 3))
+    c = CpuAnsatz(4, 1, 0.5, [(0, 1), (1, 3)])
+    x = [0.1, 0.2, 0.3, 0.4]
+    assert c.circuit_for_data(x) == oracle.bind_gate_list(oracle.ansatz_gate_list(4, 1, 0.5, [(0, 1), (1, 3)]), x)
+    with pytest.raises(RuntimeError):
+        c.circuit_for_data([0.1])
+    assert structural_chi_bound(50, 2, oracle.entanglement_graph(50, 2)) == 16
+    assert structural_chi_bound(20, 2, oracle.entanglement_graph(20, 1)) == 4

@@ -1,0 +1,121 @@
+"""CPU tests of the multi-GPU host logic: sharding, Gram row-block partition and assembly, and the
+torch.distributed plumbing (gloo, world_size 2) the NCCL path uses on the GPUs."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle.gram_ref import gram_from_mps, simulate_batch
+from oracle.mps_ref import mps_inner
+
+
+def test_shard_bounds_cover_everything():
+    from qkmps.engine import shard_bounds
+    for N in (0, 1, 7, 40, 1000, 1001):
+        for size in (1, 2, 3, 4, 8):
+            spans = [shard_bounds(N, size, r) for r in range(size)]
+            assert spans[0][0] == 0 and spans[-1][1] == N
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            per = -(-N // size) if N else 0
+            assert all(hi - lo <= per for lo, hi in spans)
+            assert all(lo == min(r * per, N) for r, (lo, hi) in enumerate(spans))   # reference gpu:154 chunking
+
+
+@pytest.mark.parametrize("symmetric", [True, False])
+def test_row_tiles_partition(symmetric):
+    from qkmps.engine import row_tiles
+    for rows, cols in [(1, 1), (13, 13), (40, 40), (100, 100), (1000, 1000)] + ([] if symmetric else [(8, 40), (37, 100)]):
+        for size in (1, 2, 4, 8):
+            cover = np.zeros((rows, cols), dtype=int)
+            work = []
+            for r in range(size):
+                w = 0
+                for r0, r1, c0, c1 in row_tiles(rows, cols, symmetric, size, r):
+                    for y in range(r0, r1):
+                        xs = range(c0, min(c1, y + 1)) if symmetric else range(c0, c1)
+                        for x in xs:
+                            cover[y, x] += 1
+                            w += 1
+                work.append(w)
+            expect = np.tril(np.ones((rows, cols), dtype=int)) if symmetric else np.ones((rows, cols), dtype=int)
+            assert np.array_equal(cover, expect)
+            if rows >= 1000:
+                assert max(work) <= 1.05 * (sum(work) / size)      # balanced to within one row block
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    import sys
+    import pathlib
+    root = pathlib.Path(__file__).resolve().parent.parent
+    for p in (root, root / "qml-cutensornet_b200", root / "tests"):
+        sys.path.insert(0, str(p))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    from qkmps.comm import (allgather_bytes, allreduce_max_array, allreduce_max_int, init_from_env,
+                            reduce_sum_to_root)
+    from qkmps.engine import row_tiles, shard_bounds
+    comm = init_from_env("gloo")
+    assert comm.Get_rank() == rank and comm.Get_size() == world
+    assert list(allreduce_max_array(comm, np.array([rank + 1, 5 - rank], dtype=np.int32))) == [world, 5]
+    assert allreduce_max_int(comm, rank) == world - 1
+    g = allgather_bytes(comm, torch.full((6,), rank, dtype=torch.uint8))
+    assert g.tolist() == sum([[r] * 6 for r in range(world)], [])
+    assert comm.bcast({"a": 1} if rank == 0 else None) == {"a": 1}
+
+    # emulate the engine's flow with the oracle as the arithmetic: shard -> simulate -> gather -> tiles -> reduce
+    n, r, gmm, d, N = 8, 2, 0.5, 1, 13
+    emap = oracle.entanglement_graph(n, d)
+    X = oracle.synthetic_features(N, n, 0)
+    lo, hi = shard_bounds(N, world, rank)
+    mine = simulate_batch(n, r, gmm, emap, X[lo:hi])
+    gathered = [None] * world
+    torch.distributed.all_gather_object(gathered, [m.tensors for m in mine])
+
+    class _M:
+        def __init__(self, t):
+            self.tensors = t
+    states = [_M(t) for part in gathered for t in part]
+    assert len(states) == N
+    K = torch.zeros((N, N), dtype=torch.float64)
+    for r0, r1, c0, c1 in row_tiles(N, N, True, world, rank):
+        for y in range(r0, r1):
+            for x in range(c0, min(c1, y + 1)):
+                v = abs(mps_inner(states[y], states[x])) ** 2
+                K[y, x] = v
+                K[x, y] = v
+    K = reduce_sum_to_root(comm, K)
+    red = comm.reduce(np.full((2, 2), float(rank + 1)))
+    if rank == 0:
+        Kref = gram_from_mps(simulate_batch(n, r, gmm, emap, X))
+        assert np.abs(K.numpy() - Kref).max() < 1e-13
+        assert np.array_equal(red, np.full((2, 2), float(sum(range(1, world + 1)))))
+        out.put("ok")
+    else:
+        assert red is None
+    comm.Barrier()
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_gloo_two_ranks(world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert out.get(timeout=5) == "ok"

@@ -154,7 +154,10 @@ def test_config3_shape_against_oracle(qk, cuda_device):
         refchi = np.array([[1] + m.bond_dims() + [1] for m in ref])
         Kref = gram_from_mps(ref)
         assert np.abs(K - Kref).max() < TOL
-        assert int(refchi.max()) <= 16 and int(prof["info_x"]["chi"].max()) <= 16   # structural bound 2^(r*cover(d))
+        # structural bound 2^(r*cover(d)) = 16.  (The numpy restatement of the pytket rule compares a
+        # sequential running sum with a pairwise-summed total and can keep rounding-noise values at
+        # gamma = 1 -- refchi up to 26 -- which is why only the CUDA path's chi is bounded here.)
+        assert int(prof["info_x"]["chi"].max()) <= 16
         # ITensors rule through the other entry point: same truncation decisions as the oracle
         from cpu_backend.kernel_state_ansatz import build_kernel_matrix as bkm_cpu
         K0 = bkm_cpu(SingleComm(), ans, X, info_file="/tmp/qk_c3", truncation_error=1e-16)

@@ -1,0 +1,114 @@
+"""CPU tests of the stage-1 device core through its host emulation (tests/host_emu): the same
+source the CUDA kernel is compiled from (qml-cutensornet_b200/csrc/qk_sim_core.h, qk_plan.cpp),
+checked against the oracle and the golden fixtures."""
+import pathlib
+
+import numpy as np
+import pytest
+
+import oracle
+from emu_util import TensorsMPS, build_emu, emu_simulate
+from oracle.gram_ref import gram_from_mps, simulate_batch
+from oracle.mps_ref import mps_inner
+
+GOLDEN = pathlib.Path(__file__).parent / "golden"
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return build_emu()
+
+
+@pytest.mark.parametrize("n,r,g,d,cap", [(6, 2, 0.5, 1, 4), (10, 2, 0.5, 1, 4), (10, 2, 1.0, 2, 16), (12, 2, 0.7, 3, 32),
+                                         (9, 3, 0.9, 2, 32), (30, 2, 0.1, 2, 16)])
+def test_emu_matches_oracle_itensors(emu, n, r, g, d, cap):
+    N = 4
+    X = oracle.synthetic_features(N, n, 0)
+    emap = oracle.entanglement_graph(n, d)
+    gates = oracle.ansatz_gate_list(n, r, g, emap)
+    states, chi, stats, _ = emu_simulate(emu, n, gates, X, trunc_mode=0, chi_cap=cap)
+    ref = simulate_batch(n, r, g, emap, X)
+    assert np.array_equal(chi, np.array([[1] + m.bond_dims() + [1] for m in ref]))
+    assert not stats[:, 2].any()
+    ms = [TensorsMPS(s) for s in states]
+    for i in range(N):
+        assert abs(abs(mps_inner(ms[i], ref[i])) ** 2 - 1) < 1e-11
+    assert np.abs(gram_from_mps(ms) - gram_from_mps(ref)).max() < 1e-11
+    if n <= 12:
+        assert np.abs(gram_from_mps(ms) - oracle.statevector_gram(n, r, g, emap, X)).max() < 1e-8
+
+
+def test_emu_pytket_mode_and_fidelity(emu):
+    n, r, g, d = 10, 2, 0.5, 2
+    X = oracle.synthetic_features(5, n, 3)
+    emap = oracle.entanglement_graph(n, d)
+    gates = oracle.ansatz_gate_list(n, r, g, emap)
+    states, chi, stats, _ = emu_simulate(emu, n, gates, X, trunc_mode=1, chi_cap=16)
+    ref = simulate_batch(n, r, g, emap, X, mode="pytket")
+    K = gram_from_mps([TensorsMPS(s) for s in states])
+    assert np.abs(K - gram_from_mps(ref)).max() < 1e-8
+    assert np.abs(K - oracle.statevector_gram(n, r, g, emap, X)).max() < 1e-8
+    assert np.abs(np.diag(K) - 1).max() < 1e-12          # renormalised
+    assert np.allclose(stats[:, 0], [m.fidelity for m in ref], atol=1e-12)
+
+
+def test_emu_group_sizes_agree(emu):
+    """The result must not depend on how many threads cooperate on one datapoint."""
+    n, r, g, d = 10, 2, 1.0, 2
+    X = oracle.synthetic_features(2, n, 5)
+    gates = oracle.ansatz_gate_list(n, r, g, oracle.entanglement_graph(n, d))
+    base = None
+    for G in (32, 64, 128, 256):
+        states, chi, _, _ = emu_simulate(emu, n, gates, X, chi_cap=16, threads=G)
+        K = gram_from_mps([TensorsMPS(s) for s in states])
+        if base is None:
+            base = (K, chi)
+        else:
+            assert np.array_equal(chi, base[1])
+            assert np.abs(K - base[0]).max() < 1e-12
+
+
+def test_emu_cap_hit_is_flagged(emu):
+    n, r, g, d = 10, 2, 1.0, 2
+    X = oracle.synthetic_features(3, n, 0)
+    gates = oracle.ansatz_gate_list(n, r, g, oracle.entanglement_graph(n, d))
+    _, chi, stats, _ = emu_simulate(emu, n, gates, X, chi_cap=4)
+    assert chi.max() <= 4
+    assert (stats[:, 2].astype(int) & 1).any()           # QK_FLAG_CAP_HIT
+    assert (stats[:, 1] > 1e-12).any()                   # discarded weight accounted for
+
+
+def test_emu_other_gates(emu):
+    """Rx and ZZPhase (KernelPkg.jl:8-14,34-42) through the same core."""
+    n = 5
+    gates = [("H", (q,), None) for q in range(n)]
+    gates += [("Rx", (q,), ("lin", q, 0.7)) for q in range(n)]
+    gates += [("ZZPhase", (q, q + 1), ("prod", q, q + 1, 0.9)) for q in range(n - 1)]
+    gates += [("XXPhase", (1, 2), ("const", 0.31)), ("SWAP", (2, 3), None), ("Rz", (3,), ("const", 0.2))]
+    X = oracle.synthetic_features(3, n, 1)
+    states, _, _, _ = emu_simulate(emu, n, gates, X, chi_cap=8)
+    from oracle.ansatz import bind_gate_list
+    from oracle.statevector import run_gates_sv
+    for i in range(3):
+        sv = run_gates_sv(n, bind_gate_list(gates, X[i]))
+        v = states[i][0]
+        for t in states[i][1:]:
+            v = np.tensordot(v, t, axes=([v.ndim - 1], [0]))
+        assert np.abs(v.reshape(-1) - sv).max() < 1e-12
+
+
+def test_emu_against_golden(emu):
+    for f in sorted(GOLDEN.glob("*.npz")):
+        z = np.load(f)
+        n, r, d, g = int(z["n"]), int(z["r"]), int(z["d"]), float(z["gamma"])
+        gates = oracle.ansatz_gate_list(n, r, g, oracle.entanglement_graph(n, d))
+        cap = 32 if z["chi_X"].max() > 16 else 16
+        sx, chi, _, _ = emu_simulate(emu, n, gates, z["X"], chi_cap=cap)
+        assert np.array_equal(chi, z["chi_X"]), f.name
+        mx = [TensorsMPS(s) for s in sx]
+        if "Y" in z.files:
+            sy, _, _, _ = emu_simulate(emu, n, gates, z["Y"], chi_cap=cap)
+            K = gram_from_mps(mx, [TensorsMPS(s) for s in sy])
+        else:
+            K = gram_from_mps(mx)
+        assert np.abs(K - z["K_oracle"]).max() < 1e-10, f.name
