@@ -55,6 +55,12 @@ typedef enum {
                             renormalise, track fidelity (gpu_backend/kernel_state_ansatz.py:141-144) */
 } qk_trunc_mode;
 
+/* plan flags */
+#define QK_PLAN_DEFAULT 0
+#define QK_PLAN_LITERAL_ORDER 1   /* keep the gate list's order of the (mutually commuting) XXPhase / ZZPhase
+                                     interactions; default: each run of them is applied as one sweep so the
+                                     orthogonality centre never has to jump (same unitary, fewer gauge moves) */
+
 typedef struct qk_plan qk_plan;     /* compiled static op schedule of one ansatz (host object) */
 typedef struct qk_batch qk_batch;   /* device-resident batch of simulated MPS */
 
@@ -79,11 +85,11 @@ int qk_device_count(int* count);
 /* ---- plan: replaces KernelStateAnsatz's circuit + routing and the per-gate bookkeeping of the
  *      third-party simulators (gpu_backend/kernel_state_ansatz.py:53-90; main.py:21-45,73). ---- */
 int qk_plan_create_gates(int n_qubits, const qk_gate* gates, int n_gates,
-                         int trunc_mode, double trunc_error, int chi_cap, qk_plan** out);
+                         int trunc_mode, double trunc_error, int chi_cap, int flags, qk_plan** out);
 /* builds H / Rz / routed XXPhase from the ansatz parameters, then compiles it */
 int qk_plan_create_ansatz(int n_qubits, int reps, double gamma, int hadamard_init,
                           const int32_t* pairs /*[n_pairs][2]*/, int n_pairs,
-                          int trunc_mode, double trunc_error, int chi_cap, qk_plan** out);
+                          int trunc_mode, double trunc_error, int chi_cap, int flags, qk_plan** out);
 int qk_plan_info(const qk_plan* plan, qk_plan_info_t* info);
 int qk_plan_ops(const qk_plan* plan, qk_op_view* ops, int max_ops);   /* returns number written */
 void qk_plan_destroy(qk_plan* plan);

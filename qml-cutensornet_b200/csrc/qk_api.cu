@@ -120,19 +120,19 @@ int qk_device_count(int* count) {
 
 // ---------------------------------------------------------------- plan
 int qk_plan_create_gates(int n_qubits, const qk_gate* gates, int n_gates, int trunc_mode, double trunc_error,
-                         int chi_cap, qk_plan** out) {
+                         int chi_cap, int flags, qk_plan** out) {
   if (!out) return fail(QK_ERR_ARG, "out is NULL");
   *out = nullptr;
   qk_plan* p = new qk_plan();
   std::string err;
-  int rc = qk_compile_plan(n_qubits, gates, n_gates, trunc_mode, trunc_error, chi_cap, p, &err);
+  int rc = qk_compile_plan(n_qubits, gates, n_gates, trunc_mode, trunc_error, chi_cap, flags, p, &err);
   if (rc != QK_OK) { delete p; return fail(rc, err); }
   *out = p;
   return QK_OK;
 }
 
 int qk_plan_create_ansatz(int n_qubits, int reps, double gamma, int hadamard_init, const int32_t* pairs, int n_pairs,
-                          int trunc_mode, double trunc_error, int chi_cap, qk_plan** out) {
+                          int trunc_mode, double trunc_error, int chi_cap, int flags, qk_plan** out) {
   if (!out) return fail(QK_ERR_ARG, "out is NULL");
   *out = nullptr;
   if (n_pairs > 0 && !pairs) return fail(QK_ERR_ARG, "pairs is NULL");
@@ -140,7 +140,7 @@ int qk_plan_create_ansatz(int n_qubits, int reps, double gamma, int hadamard_ini
   std::string err;
   int rc = qk_ansatz_gates(n_qubits, reps, gamma, hadamard_init, pairs, n_pairs, &gates, &err);
   if (rc != QK_OK) return fail(rc, err);
-  return qk_plan_create_gates(n_qubits, gates.data(), (int)gates.size(), trunc_mode, trunc_error, chi_cap, out);
+  return qk_plan_create_gates(n_qubits, gates.data(), (int)gates.size(), trunc_mode, trunc_error, chi_cap, flags, out);
 }
 
 int qk_plan_info(const qk_plan* plan, qk_plan_info_t* info) {

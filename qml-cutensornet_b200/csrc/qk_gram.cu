@@ -11,6 +11,10 @@
 // so the site tensors are stored in HBM already permuted into A-fragment order ("frag" layout,
 // written by qk_pack_kernel) and arrive in shared memory through a 3-stage cp.async.bulk (TMA)
 // + mbarrier pipeline fed by a dedicated producer warp.
+//   * every bond index is stored permuted inside its group of 8 (logical 8t+4e+j <-> physical
+//     8t+2j+e) so that the even / odd k-blocks of a tile hold logical indices 8t..8t+3 / 8t+4..8t+7:
+//     a state whose bond dimension is <= 8t+4 skips the odd k-block (contraction granularity 4).
+//   * complex products use 3 real MMAs (S1 = Ar Br, S2 = Ai Bi, S3 = (Ar +- Ai)(Br + Bi)) instead of 4.
 //
 // qk_gram_store_kernel -- CUDA-core FP64 cross-check on the unpadded stores (any chi); used by
 // tests and as the path for bond dimensions above 16.
@@ -39,7 +43,10 @@ void qk_frag_layout(int n, const int32_t* D, FragLayout* L, int64_t* site_off_by
 // ------------------------------------------------------------------------------------------------
 // pack: unpadded store -> frag layout
 //   block(s) doubles index d:  e = d&1, lane = (d>>1)&31, h = (d>>6)&1, kt, mt, p from d>>7
-//   value = Re/Im (h) of A[c = 8kt + 2(lane&3) + e][p][c' = 8mt + (lane>>2)]   (0 outside chi)
+//   value = Re/Im (h) of A[c][p][c'] with the LOGICAL bond indices
+//       c  = 8kt + 4e + (lane&3)                      (physical column 8kt + 2(lane&3) + e)
+//       c' = 8mt + 4((lane>>2)&1) + (lane>>3)         (physical row    8mt + (lane>>2))
+//   (0 outside chi).  Trailer: n+1 bytes ceil(chi_b / 4) = live k-blocks of bond b.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) qk_pack_kernel(int n, const c128* __restrict__ store, int64_t state_stride,
                                                       const int64_t* __restrict__ site_off,
@@ -60,8 +67,9 @@ __global__ void __launch_bounds__(256) qk_pack_kernel(int n, const c128* __restr
     const int kt = rest % KT; rest /= KT;
     const int mt = rest % MT;
     const int p = rest / MT;
-    const int cidx = 8 * kt + 2 * (lane & 3) + e;
-    const int cp = 8 * mt + (lane >> 2);
+    const int cidx = 8 * kt + 4 * e + (lane & 3);
+    const int g = lane >> 2;
+    const int cp = 8 * mt + 4 * (g & 1) + (g >> 1);
     double v = 0.0;
     if (cidx < cl && cp < cr) {
       const c128 a = A[(size_t)(cidx * 2 + p) * cr + cp];
@@ -71,7 +79,7 @@ __global__ void __launch_bounds__(256) qk_pack_kernel(int n, const c128* __restr
   }
   if (s == 0) {
     unsigned char* tc = frag + (size_t)i * frag_stride + frag_data;
-    for (int b = threadIdx.x; b <= n; b += blockDim.x) tc[b] = (unsigned char)((chi[(size_t)i * (n + 1) + b] + 7) >> 3);
+    for (int b = threadIdx.x; b <= n; b += blockDim.x) tc[b] = (unsigned char)((chi[(size_t)i * (n + 1) + b] + 3) >> 2);
   }
 }
 
@@ -195,12 +203,15 @@ __global__ void __launch_bounds__((QK_GRAM_WARPS + 1) * 32, 1) qk_gram_dmma_kern
   const unsigned char* tcx = stc + ti * (n + 1);
   const unsigned char* tcy = stc + (QK_TI + tj) * (n + 1);
 
-  double Er[NT][NT][2], Ei[NT][NT][2];   // E[bra tile][ket tile]
+  // E[bra tile][ket tile]: real part, imaginary part and their sum (3M complex products)
+  double Er[NT][NT][2], Ei[NT][NT][2], Es[NT][NT][2];
 #pragma unroll
   for (int a = 0; a < NT; ++a)
 #pragma unroll
-    for (int b = 0; b < NT; ++b) { Er[a][b][0] = Er[a][b][1] = 0.0; Ei[a][b][0] = Ei[a][b][1] = 0.0; }
-  if (lane == 0) Er[0][0][0] = 1.0;   // E_0 = [1]
+    for (int b = 0; b < NT; ++b) {
+      Er[a][b][0] = Er[a][b][1] = 0.0; Ei[a][b][0] = Ei[a][b][1] = 0.0; Es[a][b][0] = Es[a][b][1] = 0.0;
+    }
+  if (lane == 0) { Er[0][0][0] = 1.0; Es[0][0][0] = 1.0; }   // E_0 = [1]
 
   for (int s = 0; s < n; ++s) {
     const int st = s % QK_NS;
@@ -209,70 +220,91 @@ __global__ void __launch_bounds__((QK_GRAM_WARPS + 1) * 32, 1) qk_gram_dmma_kern
     if (active) {
       const int KTx = sDx[s] >> 3, MTx = sDx[s + 1] >> 3;
       const int KTy = sDy[s] >> 3, MTy = sDy[s + 1] >> 3;
-      const int kx = tcx[s], mx = tcx[s + 1], ky = tcy[s], my = tcy[s + 1];
+      // live k-blocks (of 4) on the contraction side, live 8-tiles on the output side
+      const int kbx = tcx[s], kby = tcy[s];
+      const int mx = (tcx[s + 1] + 1) >> 1, my = (tcy[s + 1] + 1) >> 1, ky = (kby + 1) >> 1;
       const unsigned char* sb = stage0 + (size_t)st * stage_bytes;
       const double2* bx = (const double2*)(sb + (size_t)ti * P.slot_x);
       const double2* by = (const double2*)(sb + (size_t)QK_TI * P.slot_x + (size_t)tj * P.slot_y);
-      double Fr[NT][NT][2], Fi[NT][NT][2];
+      double F1[NT][NT][2], F2[NT][NT][2], F3[NT][NT][2];   // E' as S1, S2, S3 over both p
 #pragma unroll
       for (int a = 0; a < NT; ++a)
 #pragma unroll
-        for (int b = 0; b < NT; ++b) { Fr[a][b][0] = Fr[a][b][1] = 0.0; Fi[a][b][0] = Fi[a][b][1] = 0.0; }
+        for (int b = 0; b < NT; ++b) {
+          F1[a][b][0] = F1[a][b][1] = 0.0; F2[a][b][0] = F2[a][b][1] = 0.0; F3[a][b][0] = F3[a][b][1] = 0.0;
+        }
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
-        double Tr[NT][NT][2], Ti[NT][NT][2];   // T^T[ket-right tile][bra-left tile]
+        // T^T[ket-right tile][bra-left tile] as S1 = Ar Er, S2 = Ai Ei, S3 = (Ar+Ai)(Er+Ei)
+        double T1[NT][NT][2], T2[NT][NT][2], T3[NT][NT][2];
 #pragma unroll
         for (int a = 0; a < NT; ++a)
 #pragma unroll
-          for (int b = 0; b < NT; ++b) { Tr[a][b][0] = Tr[a][b][1] = 0.0; Ti[a][b][0] = Ti[a][b][1] = 0.0; }
+          for (int b = 0; b < NT; ++b) {
+            T1[a][b][0] = T1[a][b][1] = 0.0; T2[a][b][0] = T2[a][b][1] = 0.0; T3[a][b][0] = T3[a][b][1] = 0.0;
+          }
         // step 1: T^T[c'][a] += sum_c A_x[c,p,c'] * E[a][c]
 #pragma unroll
         for (int mt = 0; mt < NT; ++mt) {
           if (mt < mx) {
 #pragma unroll
             for (int kt = 0; kt < NT; ++kt) {
-              if (kt < kx) {
+              if (2 * kt < kbx) {
                 const int fi = (((p * MTx + mt) * KTx + kt) * 2) * 32 + lane;
                 const double2 mr = bx[fi], mi = bx[fi + 32];
-                const double n0 = -mi.x, n1 = -mi.y;
+                const double s0 = mr.x + mi.x, s1 = mr.y + mi.y;
+                const bool odd = (2 * kt + 1 < kbx);
 #pragma unroll
                 for (int at = 0; at < NT; ++at) {
                   if (at < ky) {
-                    qk_dmma(Tr[mt][at], mr.x, Er[at][kt][0]);
-                    qk_dmma(Ti[mt][at], mr.x, Ei[at][kt][0]);
-                    qk_dmma(Tr[mt][at], n0, Ei[at][kt][0]);
-                    qk_dmma(Ti[mt][at], mi.x, Er[at][kt][0]);
-                    qk_dmma(Tr[mt][at], mr.y, Er[at][kt][1]);
-                    qk_dmma(Ti[mt][at], mr.y, Ei[at][kt][1]);
-                    qk_dmma(Tr[mt][at], n1, Ei[at][kt][1]);
-                    qk_dmma(Ti[mt][at], mi.y, Er[at][kt][1]);
+                    qk_dmma(T1[mt][at], mr.x, Er[at][kt][0]);
+                    qk_dmma(T2[mt][at], mi.x, Ei[at][kt][0]);
+                    qk_dmma(T3[mt][at], s0, Es[at][kt][0]);
+                    if (odd) {
+                      qk_dmma(T1[mt][at], mr.y, Er[at][kt][1]);
+                      qk_dmma(T2[mt][at], mi.y, Ei[at][kt][1]);
+                      qk_dmma(T3[mt][at], s1, Es[at][kt][1]);
+                    }
                   }
                 }
               }
             }
           }
         }
-        // step 2: E'[b'][c'] += sum_a conj(A_y[a,p,b']) * T[a][c']
+        // T = (S1 - S2) + i (S3 - S1 - S2);  reuse T1 = Tr, T2 = Ti, T3 = Tr + Ti
+#pragma unroll
+        for (int a = 0; a < NT; ++a)
+#pragma unroll
+          for (int b = 0; b < NT; ++b)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const double u1 = T1[a][b][e], u2 = T2[a][b][e], u3 = T3[a][b][e];
+              T1[a][b][e] = u1 - u2;
+              T2[a][b][e] = u3 - u1 - u2;
+              T3[a][b][e] = u3 - 2.0 * u2;
+            }
+        // step 2: E'[b'][c'] += sum_a conj(A_y[a,p,b']) * T[a][c']:  S1 = Ar Tr, S2 = Ai Ti, S3 = (Ar-Ai)(Tr+Ti)
 #pragma unroll
         for (int bt = 0; bt < NT; ++bt) {
           if (bt < my) {
 #pragma unroll
             for (int at = 0; at < NT; ++at) {
-              if (at < ky) {
+              if (2 * at < kby) {
                 const int fi = (((p * MTy + bt) * KTy + at) * 2) * 32 + lane;
                 const double2 mr = by[fi], mi = by[fi + 32];
-                const double n0 = -mi.x, n1 = -mi.y;
+                const double d0 = mr.x - mi.x, d1 = mr.y - mi.y;
+                const bool odd = (2 * at + 1 < kby);
 #pragma unroll
                 for (int ct = 0; ct < NT; ++ct) {
                   if (ct < mx) {
-                    qk_dmma(Fr[bt][ct], mr.x, Tr[ct][at][0]);
-                    qk_dmma(Fi[bt][ct], mr.x, Ti[ct][at][0]);
-                    qk_dmma(Fr[bt][ct], mi.x, Ti[ct][at][0]);
-                    qk_dmma(Fi[bt][ct], n0, Tr[ct][at][0]);
-                    qk_dmma(Fr[bt][ct], mr.y, Tr[ct][at][1]);
-                    qk_dmma(Fi[bt][ct], mr.y, Ti[ct][at][1]);
-                    qk_dmma(Fr[bt][ct], mi.y, Ti[ct][at][1]);
-                    qk_dmma(Fi[bt][ct], n1, Tr[ct][at][1]);
+                    qk_dmma(F1[bt][ct], mr.x, T1[ct][at][0]);
+                    qk_dmma(F2[bt][ct], mi.x, T2[ct][at][0]);
+                    qk_dmma(F3[bt][ct], d0, T3[ct][at][0]);
+                    if (odd) {
+                      qk_dmma(F1[bt][ct], mr.y, T1[ct][at][1]);
+                      qk_dmma(F2[bt][ct], mi.y, T2[ct][at][1]);
+                      qk_dmma(F3[bt][ct], d1, T3[ct][at][1]);
+                    }
                   }
                 }
               }
@@ -280,13 +312,18 @@ __global__ void __launch_bounds__((QK_GRAM_WARPS + 1) * 32, 1) qk_gram_dmma_kern
           }
         }
       }
+      // E' = (S1 + S2) + i (S3 - S1 + S2)
 #pragma unroll
       for (int a = 0; a < NT; ++a)
 #pragma unroll
-        for (int b = 0; b < NT; ++b) {
-          Er[a][b][0] = Fr[a][b][0]; Er[a][b][1] = Fr[a][b][1];
-          Ei[a][b][0] = Fi[a][b][0]; Ei[a][b][1] = Fi[a][b][1];
-        }
+        for (int b = 0; b < NT; ++b)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const double u1 = F1[a][b][e], u2 = F2[a][b][e], u3 = F3[a][b][e];
+            Er[a][b][e] = u1 + u2;
+            Ei[a][b][e] = u3 - u1 + u2;
+            Es[a][b][e] = u3 + 2.0 * u2;
+          }
     }
     __syncwarp();
     if (lane == 0) qk_mbar_arrive(qk_smem_u32(&bars[QK_NS + st]));

@@ -11,8 +11,14 @@
 #include "qk_plan.h"
 #include "qk_sim_core.h"
 #include <math.h>
+#include <stdlib.h>
+#include <algorithm>
 
 int qk_pick_threads(int chi_cap) {
+  if (const char* e = getenv("QK_SIM_THREADS")) {   // tuning / experiments only
+    const int g = atoi(e);
+    if (g == 32 || g == 64 || g == 128 || g == 256) return g;
+  }
   if (chi_cap <= 4) return 32;
   if (chi_cap <= 8) return 64;
   if (chi_cap <= 16) return 128;
@@ -45,10 +51,78 @@ int qk_ansatz_gates(int n, int reps, double gamma, int hadamard_init, const int3
   return QK_OK;
 }
 
-int qk_compile_plan(int n, const qk_gate* gates, int n_gates, int trunc_mode, double trunc_error, int chi_cap,
-                    qk_plan* plan, std::string* err) {
+// ------------------------------------------------------------------------------------------------
+// Commutation-aware reordering.  A routed interaction  SWAP(q0,q0+1) .. SWAP(q1-2,q1-1), G(q1-1,q1),
+// SWAP(q1-2,q1-1) .. SWAP(q0,q0+1)  (gpu_backend/kernel_state_ansatz.py:78-88) acts as G on the logical
+// pair (q0, q1) and leaves every qubit in place.  All XXPhase interactions commute with each other
+// (functions of X operators only), likewise all ZZPhase ones, so a maximal run of
+// such units may be applied in any order.  The reference has no canonical order either (pytket's
+// get_commands() is a topological sort and pytket-cutensornet re-sorts gates).  We order each run as
+// one sweep, left-to-right or right-to-left depending on where the previous run ended, which keeps
+// the orthogonality centre adjacent to every gate and removes nearly all gauge moves.
+// ------------------------------------------------------------------------------------------------
+struct QkUnit { int first, count; int kind; int lo, hi; };   // gates [first, first+count)
+
+static void qk_reorder_commuting(std::vector<qk_gate>& g) {
+  const int ng = (int)g.size();
+  std::vector<QkUnit> units;
+  for (int i = 0; i < ng;) {
+    int k = 0;
+    const int q0 = g[i].q0;
+    while (i + k < ng && g[i + k].kind == QK_GATE_SWAP && g[i + k].q0 == q0 + k && g[i + k].q1 == q0 + k + 1) ++k;
+    bool ok = false;
+    const int c = i + k;   // candidate centre gate
+    if (c < ng && (g[c].kind == QK_GATE_XX || g[c].kind == QK_GATE_ZZ) && g[c].q1 == g[c].q0 + 1 &&
+        (k == 0 || g[c].q0 == q0 + k) && c + k < ng) {
+      ok = true;
+      for (int j = 0; ok && j < k; ++j) {
+        const int idx = c + 1 + j;
+        if (idx >= ng || g[idx].kind != QK_GATE_SWAP || g[idx].q0 != q0 + k - 1 - j || g[idx].q1 != q0 + k - j) ok = false;
+      }
+    }
+    if (ok) {
+      QkUnit u; u.first = i; u.count = 2 * k + 1; u.kind = g[c].kind; u.lo = (k == 0) ? g[c].q0 : q0; u.hi = g[c].q1;
+      units.push_back(u);
+      i += u.count;
+    } else {
+      QkUnit u; u.first = i; u.count = 1; u.kind = -1; u.lo = g[i].q0; u.hi = g[i].q0;
+      units.push_back(u);
+      i += 1;
+    }
+  }
+  std::vector<qk_gate> out;
+  out.reserve(ng);
+  int last_pos = 0;   // where the previous run of interactions ended (site index)
+  const int n_units = (int)units.size();
+  for (int u = 0; u < n_units;) {
+    if (units[u].kind < 0) {
+      out.push_back(g[units[u].first]);
+      ++u;
+      continue;
+    }
+    int v = u;
+    while (v < n_units && units[v].kind == units[u].kind) ++v;
+    std::vector<QkUnit> run(units.begin() + u, units.begin() + v);
+    int lo_min = run[0].lo, hi_max = run[0].hi;
+    for (const QkUnit& r : run) { if (r.lo < lo_min) lo_min = r.lo; if (r.hi > hi_max) hi_max = r.hi; }
+    const bool ascending = (last_pos - lo_min) <= (hi_max - last_pos);
+    std::stable_sort(run.begin(), run.end(), [ascending](const QkUnit& a, const QkUnit& b) {
+      if (a.lo != b.lo) return ascending ? a.lo < b.lo : a.lo > b.lo;
+      return ascending ? a.hi < b.hi : a.hi > b.hi;
+    });
+    for (const QkUnit& r : run)
+      for (int j = 0; j < r.count; ++j) out.push_back(g[r.first + j]);
+    last_pos = run.back().lo;
+    u = v;
+  }
+  g.swap(out);
+}
+
+int qk_compile_plan(int n, const qk_gate* gates_in, int n_gates, int trunc_mode, double trunc_error, int chi_cap,
+                    int flags, qk_plan* plan, std::string* err) {
+  plan->reorder = (flags & QK_PLAN_LITERAL_ORDER) ? 0 : 1;
   if (n < 1) { *err = "n_qubits must be >= 1"; return QK_ERR_ARG; }
-  if (n_gates < 0 || (n_gates > 0 && !gates)) { *err = "bad gate list"; return QK_ERR_ARG; }
+  if (n_gates < 0 || (n_gates > 0 && !gates_in)) { *err = "bad gate list"; return QK_ERR_ARG; }
   if (trunc_mode != QK_TRUNC_ITENSORS && trunc_mode != QK_TRUNC_PYTKET) { *err = "bad truncation mode"; return QK_ERR_ARG; }
   if (!(trunc_error >= 0.0) || trunc_error >= 1.0) { *err = "truncation_error must be in [0, 1)"; return QK_ERR_ARG; }
   if (chi_cap < 1) { *err = "chi_cap must be >= 1"; return QK_ERR_ARG; }
@@ -58,6 +132,17 @@ int qk_compile_plan(int n, const qk_gate* gates, int n_gates, int trunc_mode, do
   }
   plan->n = n; plan->n_gates = n_gates; plan->trunc_mode = trunc_mode; plan->trunc_error = trunc_error;
   plan->ops.clear(); plan->n_2q = plan->n_1q = plan->n_moves = 0;
+  std::vector<qk_gate> gate_vec(gates_in, gates_in + n_gates);
+  for (int i = 0; i < n_gates; ++i) {   // validate before touching the order
+    const qk_gate& g = gate_vec[i];
+    const bool two = (g.kind == QK_GATE_XX || g.kind == QK_GATE_ZZ || g.kind == QK_GATE_SWAP);
+    const bool one = (g.kind == QK_GATE_H || g.kind == QK_GATE_RZ || g.kind == QK_GATE_RX);
+    if (!one && !two) { *err = "Unrecognised gate."; return QK_ERR_ARG; }
+    if (g.q0 < 0 || g.q0 >= n) { *err = "gate qubit out of range"; return QK_ERR_ARG; }
+    if (two && (g.q1 != g.q0 + 1 || g.q1 >= n)) { *err = "two-qubit gates must act on adjacent sites (q, q+1)"; return QK_ERR_ARG; }
+  }
+  if (plan->reorder) qk_reorder_commuting(gate_vec);
+  const qk_gate* gates = gate_vec.data();
 
   // validate + find, for every 2-qubit gate, the bond of the next one
   std::vector<int> next2q(n_gates, -1);

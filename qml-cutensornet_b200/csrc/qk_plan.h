@@ -19,11 +19,12 @@ struct qk_plan {
   std::vector<int64_t> site_off;   // [n+1]
   int64_t state_stride = 0;
   int n_2q = 0, n_1q = 0, n_moves = 0;
+  int reorder = 1;                 // commutation-aware reordering of interaction runs (qk_plan.cpp)
 };
 
 // Returns 0 or a negative qk_status; err receives a message.
 int qk_compile_plan(int n_qubits, const qk_gate* gates, int n_gates, int trunc_mode, double trunc_error,
-                    int chi_cap, qk_plan* plan, std::string* err);
+                    int chi_cap, int flags, qk_plan* plan, std::string* err);
 // H / Rz / routed XXPhase gate list of the ansatz (gpu_backend/kernel_state_ansatz.py:53-90)
 int qk_ansatz_gates(int n_qubits, int reps, double gamma, int hadamard_init, const int32_t* pairs, int n_pairs,
                     std::vector<qk_gate>* out, std::string* err);

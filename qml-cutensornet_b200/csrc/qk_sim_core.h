@@ -159,10 +159,145 @@ QK_DEV bool qk_rr_pair(int i, int r, int Ce, int C, int& p, int& q) {
   // round-robin tournament: Ce (even) players, round r in [0, Ce-1), pair slot i in [0, Ce/2)
   const int m = Ce - 1;
   if (i == 0) { p = m; q = r; }
-  else { p = (r + i) % m; q = (r - i + m) % m; }
+  else {
+    p = r + i; if (p >= m) p -= m;
+    q = r - i; if (q < 0) q += m;
+  }
   if (p > q) { const int t = p; p = q; q = t; }
   return q < C;
 }
+
+QK_DEV double qk_rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+QK_DEV double qk_rcp(double x) {
+#if defined(__CUDA_ARCH__)
+  return __drcp_rn(x);
+#else
+  return 1.0 / x;
+#endif
+}
+
+// Rotation that orthogonalises columns x, y with a = |x|^2, b = |y|^2, gamma = x^dag y = (gr, gi):
+//   x' = cs x - conj(f) y ,  y' = f x + cs y ,  f = sin(theta) e^{i phi} sign(b - a),  cs = cos(theta),
+//   tan(2 theta) = 2|gamma| / |b - a|,  |theta| <= pi/4.   Returns false if no rotation is needed.
+// Written with two dependent rsqrt only (the parameter chain is the latency floor of a Jacobi round):
+//   h = sqrt((b-a)^2 + 4|gamma|^2);  cos(2 theta) = |b-a|/h;  sin(2 theta) e^{i phi} = 2 gamma / h;
+//   cos^2(theta) = (1 + cos 2theta)/2;  sin(theta) = sin(2 theta) / (2 cos(theta)).
+QK_DEV bool qk_rotation(double a, double b, double gr, double gi, double tol2, double floor2, double& cs, c128& f) {
+  const double g2 = gr * gr + gi * gi;
+  // a column whose weight is < 1e-28 of the total is numerically zero (rank-deficient theta is the
+  // common case); rotating it again only chases rounding noise
+  const bool live = (a > floor2) && (b > floor2);
+  if (!(live && g2 > tol2 * a * b && g2 > 0.0)) return false;
+  const double tau = b - a;
+  const double rh = qk_rsqrt(fma(tau, tau, 4.0 * g2));
+  const double x = fma(0.5 * fabs(tau), rh, 0.5);
+  const double rs = qk_rsqrt(x);
+  cs = x * rs;
+  const double k = (tau >= 0.0 ? rh : -rh) * rs;
+  f = cmake(k * gr, k * gi);
+  return true;
+}
+
+QK_DEV void qk_rot2(c128& xp, c128& xq, double cs, c128 f) {
+  const c128 p = xp, q = xq;
+  xp.x = fma(-f.y, q.y, fma(-f.x, q.x, cs * p.x));
+  xp.y = fma(f.y, q.x, fma(-f.x, q.y, cs * p.y));
+  xq.x = fma(-f.y, p.y, fma(f.x, p.x, cs * q.x));
+  xq.y = fma(f.y, p.x, fma(f.x, p.y, cs * q.y));
+}
+
+QK_DEV void qk_rotate_rows(c128* up, c128* uq, int rows, int sl, int tpp, double cs, c128 f) {
+  for (int row = sl; row < rows; row += tpp) {
+    c128 xp = up[row], xq = uq[row];
+    qk_rot2(xp, xq, cs, f);
+    up[row] = xp;
+    uq[row] = xq;
+  }
+}
+
+#if defined(__CUDA_ARCH__) && !defined(QK_HOST_EMU)
+// Device fast path of one (pair, round) step: the thread's <= RPT rows of both columns stay in
+// registers between the dot products and the rotation; partial sums reduced with warp shuffles.
+template <int RPT>
+__device__ __forceinline__ void qk_pair_step(c128* __restrict__ wp, c128* __restrict__ wq, c128* __restrict__ jp,
+                                             c128* __restrict__ jq, int R, int C, int sl, int tpp, bool valid,
+                                             double tol2, double floor2, int* rotated) {
+  c128 xp[RPT], xq[RPT];
+  double a = 0, b = 0, gr = 0, gi = 0;
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const int row = sl + k * tpp;
+    if (valid && row < R) { xp[k] = wp[row]; xq[k] = wq[row]; }
+    else { xp[k] = cmake(0, 0); xq[k] = cmake(0, 0); }
+    a = fma(xp[k].x, xp[k].x, fma(xp[k].y, xp[k].y, a));
+    b = fma(xq[k].x, xq[k].x, fma(xq[k].y, xq[k].y, b));
+    gr = fma(xp[k].x, xq[k].x, fma(xp[k].y, xq[k].y, gr));    // gamma = conj(xp) * xq
+    gi = fma(xp[k].x, xq[k].y, fma(-xp[k].y, xq[k].x, gi));
+  }
+  for (int off = tpp >> 1; off > 0; off >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, off);
+    b += __shfl_xor_sync(0xffffffffu, b, off);
+    gr += __shfl_xor_sync(0xffffffffu, gr, off);
+    gi += __shfl_xor_sync(0xffffffffu, gi, off);
+  }
+  double cs; c128 f;
+  if (valid && qk_rotation(a, b, gr, gi, tol2, floor2, cs, f)) {
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      const int row = sl + k * tpp;
+      if (row < R) {
+        qk_rot2(xp[k], xq[k], cs, f);
+        wp[row] = xp[k];
+        wq[row] = xq[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {     // C <= R, so the accumulated rotations need <= RPT rows too
+      const int row = sl + k * tpp;
+      if (row < C) {
+        c128 yp = jp[row], yq = jq[row];
+        qk_rot2(yp, yq, cs, f);
+        jp[row] = yp;
+        jq[row] = yq;
+      }
+    }
+    if (sl == 0) *rotated = 1;
+  }
+}
+
+// Same step for any number of rows per thread (rows are re-read for the rotation).
+__device__ __forceinline__ void qk_pair_step_generic(c128* wp, c128* wq, c128* jp, c128* jq, int R, int C, int sl,
+                                                     int tpp, bool valid, double tol2, double floor2, int* rotated) {
+  double a = 0, b = 0, gr = 0, gi = 0;
+  if (valid) {
+    for (int row = sl; row < R; row += tpp) {
+      const c128 xp = wp[row], xq = wq[row];
+      a = fma(xp.x, xp.x, fma(xp.y, xp.y, a));
+      b = fma(xq.x, xq.x, fma(xq.y, xq.y, b));
+      gr = fma(xp.x, xq.x, fma(xp.y, xq.y, gr));
+      gi = fma(xp.x, xq.y, fma(-xp.y, xq.x, gi));
+    }
+  }
+  for (int off = tpp >> 1; off > 0; off >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, off);
+    b += __shfl_xor_sync(0xffffffffu, b, off);
+    gr += __shfl_xor_sync(0xffffffffu, gr, off);
+    gi += __shfl_xor_sync(0xffffffffu, gi, off);
+  }
+  double cs; c128 f;
+  if (valid && qk_rotation(a, b, gr, gi, tol2, floor2, cs, f)) {
+    qk_rotate_rows(wp, wq, R, sl, tpp, cs, f);
+    qk_rotate_rows(jp, jq, C, sl, tpp, cs, f);
+    if (sl == 0) *rotated = 1;
+  }
+}
+#endif
 
 template <int G>
 QK_DEV void qk_jacobi(SimCtx& c, int R, int C) {
@@ -172,10 +307,12 @@ QK_DEV void qk_jacobi(SimCtx& c, int R, int C) {
   const int Ce = (C + 1) & ~1;
   const int npairs = Ce / 2;
   const int nrounds = Ce - 1;
-  int tpp = 1;
-  while (tpp * 2 * npairs <= G && tpp * 2 <= R) tpp *= 2;
+  int tpp = 1;   // threads per column pair: a power of two <= 32 so that a pair's threads share a warp
+  while (tpp * 2 * npairs <= G && tpp * 2 <= R && tpp < 32) tpp *= 2;
   const int pp = G / tpp;
   const int npass = (npairs + pp - 1) / pp;
+  const int rpt = (R + tpp - 1) / tpp;   // rows per thread
+  (void)rpt;
   const double tol2 = c.P->tol * c.P->tol;
   int sweep = 0;
   // total weight (Frobenius norm^2) -- invariant under the rotations
@@ -183,6 +320,7 @@ QK_DEV void qk_jacobi(SimCtx& c, int R, int C) {
     double s = 0.0;
     for (int i = tid; i < R * C; i += G) s += W[i].x * W[i].x + W[i].y * W[i].y;
     c.scr[tid] = s;
+    if (tid == 0) c.sh->rotated = 0;
   QK_PAR_END
   double total = 0.0;
   for (int t = 0; t < G; ++t) total += c.scr[t];
@@ -190,11 +328,25 @@ QK_DEV void qk_jacobi(SimCtx& c, int R, int C) {
   const double floor2 = 1e-28 * total;
   if (C >= 2) {
     for (; sweep < c.P->max_sweeps; ++sweep) {
-      QK_PAR_BEGIN(tid)
-        if (tid == 0) c.sh->rotated = 0;
-      QK_PAR_END
       for (int r = 0; r < nrounds; ++r) {
         for (int pass = 0; pass < npass; ++pass) {
+#if defined(__CUDA_ARCH__) && !defined(QK_HOST_EMU)
+          // device: rows kept in registers, partial dot products reduced with warp shuffles -> one barrier per round
+          QK_PAR_BEGIN(tid)
+            const int ps = tid / tpp, sl = tid - ps * tpp;
+            const int i = pass * pp + ps;
+            int p = 0, q = 0;
+            const bool valid = (i < npairs) && qk_rr_pair(i, r, Ce, C, p, q);
+            c128* wp = W + (size_t)p * ldw;
+            c128* wq = W + (size_t)q * ldw;
+            c128* jp = J + (size_t)p * C;
+            c128* jq = J + (size_t)q * C;
+            if (rpt <= 1) qk_pair_step<1>(wp, wq, jp, jq, R, C, sl, tpp, valid, tol2, floor2, &c.sh->rotated);
+            else if (rpt <= 2) qk_pair_step<2>(wp, wq, jp, jq, R, C, sl, tpp, valid, tol2, floor2, &c.sh->rotated);
+            else if (rpt <= 4) qk_pair_step<4>(wp, wq, jp, jq, R, C, sl, tpp, valid, tol2, floor2, &c.sh->rotated);
+            else qk_pair_step_generic(wp, wq, jp, jq, R, C, sl, tpp, valid, tol2, floor2, &c.sh->rotated);
+          QK_PAR_END
+#else
           QK_PAR_BEGIN(tid)
             const int ps = tid / tpp, sl = tid - ps * tpp;
             const int i = pass * pp + ps;
@@ -225,50 +377,29 @@ QK_DEV void qk_jacobi(SimCtx& c, int R, int C) {
                 const double* s4 = c.scr + 4 * (ps * tpp + t);
                 a += s4[0]; b += s4[1]; gr += s4[2]; gi += s4[3];
               }
-              const double g2 = gr * gr + gi * gi;
-              // a column whose weight is < 1e-28 of the total is numerically zero (rank-deficient theta
-              // is the common case); rotating it again only chases rounding noise
-              const bool live = (a > floor2) && (b > floor2);
-              if (live && g2 > tol2 * a * b && g2 > 0.0) {
-                const double gabs = sqrt(g2);
-                const double zeta = (b - a) / (2.0 * gabs);
-                const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                const double cs = 1.0 / sqrt(1.0 + t * t);
-                const double sn = cs * t;
-                const c128 f = cmake(sn * gr / gabs, sn * gi / gabs);   // s * e^{i phi}
-                c128* wp = W + (size_t)p * ldw;
-                c128* wq = W + (size_t)q * ldw;
-                for (int row = sl; row < R; row += tpp) {
-                  const c128 xp = wp[row], xq = wq[row];
-                  // x' = c x - s e^{-i phi} y ;  y' = s e^{i phi} x + c y
-                  wp[row] = csub(cscale(xp, cs), cmulc(xq, f));
-                  wq[row] = cadd(cmul(f, xp), cscale(xq, cs));
-                }
-                c128* jp = J + (size_t)p * C;
-                c128* jq = J + (size_t)q * C;
-                for (int row = sl; row < C; row += tpp) {
-                  const c128 xp = jp[row], xq = jq[row];
-                  jp[row] = csub(cscale(xp, cs), cmulc(xq, f));
-                  jq[row] = cadd(cmul(f, xp), cscale(xq, cs));
-                }
+              double cs; c128 f;
+              if (qk_rotation(a, b, gr, gi, tol2, floor2, cs, f)) {
+                qk_rotate_rows(W + (size_t)p * ldw, W + (size_t)q * ldw, R, sl, tpp, cs, f);
+                qk_rotate_rows(J + (size_t)p * C, J + (size_t)q * C, C, sl, tpp, cs, f);
                 if (sl == 0) c.sh->rotated = 1;
-#ifdef QK_EMU_DEBUG
-                if (sl == 0 && sweep > 40) printf("sweep %d r %d pair (%d,%d) a=%.3e b=%.3e |g|=%.3e rel=%.3e zeta=%.3e t=%.3e R=%d C=%d\n", sweep, r, p, q, a, b, gabs, gabs/sqrt(a*b), zeta, t, R, C);
-#endif
               }
             }
           QK_PAR_END
+#endif
         }
       }
       const int rot = c.sh->rotated;
       QK_BARRIER();
       if (!rot) { ++sweep; break; }
+      QK_PAR_BEGIN(tid)
+        if (tid == 0) c.sh->rotated = 0;
+      QK_PAR_END
     }
   }
   QK_PAR_BEGIN(tid)
     if (tid == 0) {
       c.sh->sweeps += sweep;
-      if (C >= 2 && sweep >= c.P->max_sweeps && c.sh->rotated) c.sh->flags |= QK_FLAG_NO_CONVERGE;
+      if (C >= 2 && sweep >= c.P->max_sweeps) c.sh->flags |= QK_FLAG_NO_CONVERGE;
     }
   QK_PAR_END
 }

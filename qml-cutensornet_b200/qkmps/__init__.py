@@ -22,6 +22,7 @@ QK_TRUNC_PYTKET = 1
 QK_FLAG_CAP_HIT = 1
 QK_FLAG_NO_CONVERGE = 2
 QK_ERR_LIMIT = -3
+QK_PLAN_LITERAL_ORDER = 1
 CHI_LIMIT = 32          # shared-memory-resident stage-1 kernel
 DMMA_D_LIMIT = 16       # register-resident tensor-core overlap kernel
 
@@ -126,22 +127,26 @@ def gates_to_c(gates):
 class Plan:
     """Compiled static op schedule of one ansatz (qk_plan)."""
 
-    def __init__(self, n_qubits, gates, trunc_mode, trunc_error, chi_cap):
+    def __init__(self, n_qubits, gates, trunc_mode, trunc_error, chi_cap, flags=None):
         self._h = ctypes.c_void_p()
         carr = gates_to_c(gates)
+        if flags is None:
+            flags = QK_PLAN_LITERAL_ORDER if os.environ.get("QK_SCHEDULE", "") == "literal" else 0
         _check(lib().qk_plan_create_gates(int(n_qubits), carr, len(gates), int(trunc_mode),
-                                          ctypes.c_double(trunc_error), int(chi_cap), ctypes.byref(self._h)))
+                                          ctypes.c_double(trunc_error), int(chi_cap), int(flags),
+                                          ctypes.byref(self._h)))
         self.n_qubits = int(n_qubits)
         self.chi_cap = int(chi_cap)
 
     @classmethod
-    def from_ansatz(cls, n_qubits, reps, gamma, pairs, hadamard_init, trunc_mode, trunc_error, chi_cap):
+    def from_ansatz(cls, n_qubits, reps, gamma, pairs, hadamard_init, trunc_mode, trunc_error, chi_cap, flags=0):
         self = cls.__new__(cls)
         self._h = ctypes.c_void_p()
         pr = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
         _check(lib().qk_plan_create_ansatz(int(n_qubits), int(reps), ctypes.c_double(gamma), int(bool(hadamard_init)),
                                            _p(pr, ctypes.c_int32), int(pr.shape[0]), int(trunc_mode),
-                                           ctypes.c_double(trunc_error), int(chi_cap), ctypes.byref(self._h)))
+                                           ctypes.c_double(trunc_error), int(chi_cap), int(flags),
+                                           ctypes.byref(self._h)))
         self.n_qubits = int(n_qubits)
         self.chi_cap = int(chi_cap)
         return self

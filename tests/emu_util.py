@@ -49,7 +49,7 @@ def build_emu() -> ctypes.CDLL:
     return lib
 
 
-def emu_simulate(lib, n, gates, X, trunc_mode=0, trunc_error=1e-16, chi_cap=16, threads=0):
+def emu_simulate(lib, n, gates, X, trunc_mode=0, trunc_error=1e-16, chi_cap=16, threads=0, flags=0):
     """Returns (list of per-state lists of site tensors, chi[N][n+1], stats[N][4], (n_ops, n_moves))."""
     X = np.ascontiguousarray(X, dtype=np.float64)
     N = X.shape[0]
@@ -57,7 +57,7 @@ def emu_simulate(lib, n, gates, X, trunc_mode=0, trunc_error=1e-16, chi_cap=16, 
     site_off = (ctypes.c_longlong * (n + 1))()
     n_ops, n_moves = ctypes.c_int(), ctypes.c_int()
     dptr = ctypes.POINTER(ctypes.c_double)
-    stride = lib.qk_emu_simulate(n, carr, len(gates), trunc_mode, ctypes.c_double(trunc_error), chi_cap, threads,
+    stride = lib.qk_emu_simulate(n, carr, len(gates), trunc_mode, ctypes.c_double(trunc_error), chi_cap, flags, threads,
                                  X.ctypes.data_as(dptr), N, X.shape[1], None, None, site_off, None,
                                  ctypes.byref(n_ops), ctypes.byref(n_moves))
     if stride < 0:
@@ -65,7 +65,7 @@ def emu_simulate(lib, n, gates, X, trunc_mode=0, trunc_error=1e-16, chi_cap=16, 
     chi = np.zeros((N, n + 1), dtype=np.int32)
     store = np.zeros((N, stride), dtype=np.complex128)
     stats = np.zeros((N, 4), dtype=np.float64)
-    rc = lib.qk_emu_simulate(n, carr, len(gates), trunc_mode, ctypes.c_double(trunc_error), chi_cap, threads,
+    rc = lib.qk_emu_simulate(n, carr, len(gates), trunc_mode, ctypes.c_double(trunc_error), chi_cap, flags, threads,
                              X.ctypes.data_as(dptr), N, X.shape[1],
                              chi.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
                              store.ctypes.data_as(dptr), site_off, stats.ctypes.data_as(dptr),

@@ -26,12 +26,12 @@ extern "C" {
 // site_off), stats as 4 doubles per datapoint (fidelity, trunc_weight, flags, sweeps).
 // Returns state_stride (>0) or a negative status.  If store == NULL only returns the stride.
 long long qk_emu_simulate(int n, const qk_gate* gates, int n_gates, int trunc_mode, double trunc_error,
-                          int chi_cap, int force_threads, const double* X, int N, int ldx,
+                          int chi_cap, int flags, int force_threads, const double* X, int N, int ldx,
                           int32_t* chi_out, double* store_out, long long* site_off_out, double* stats_out,
                           int* n_ops_out, int* n_moves_out) {
   qk_plan plan;
   std::string err;
-  int rc = qk_compile_plan(n, gates, n_gates, trunc_mode, trunc_error, chi_cap, &plan, &err);
+  int rc = qk_compile_plan(n, gates, n_gates, trunc_mode, trunc_error, chi_cap, flags, &plan, &err);
   if (rc != 0) return rc;
   if (n_ops_out) *n_ops_out = (int)plan.ops.size();
   if (n_moves_out) *n_moves_out = plan.n_moves;

@@ -35,20 +35,13 @@ def test_struct_layouts_match_header(qk):
     assert ctypes.sizeof(qk.QkPlanInfo) == 56
 
 
-def _plan(qk, n, r, g, d, cap=16, mode=0):
+def _plan(qk, n, r, g, d, cap=16, mode=0, flags=0):
     gates = oracle.ansatz_gate_list(n, r, g, oracle.entanglement_graph(n, d))
-    return qk.Plan(n, gates, mode, 1e-16, cap), gates
+    return qk.Plan(n, gates, mode, 1e-16, cap, flags), gates
 
 
-@pytest.mark.parametrize("n,r,d,n2q", [(10, 2, 1, 18), (50, 2, 2, 386), (100, 2, 2, 786), (165, 4, 4, 10360)])
-def test_plan_counts_and_schedule_invariants(qk, n, r, d, n2q):
-    plan, gates = _plan(qk, n, r, 0.5, d)
-    info = plan.info()
-    assert info.n_qubits == n and info.n_gates == len(gates)
-    assert info.n_ops_2q == n2q
-    assert info.n_ops_1q == n * (r + 1)
-    assert info.n_ops == info.n_ops_2q + info.n_ops_1q + info.n_moves
-    # replay the schedule: the orthogonality centre must sit on one of the two sites of every 2-site op
+def _replay(plan):
+    """Replay a schedule: the orthogonality centre must sit on one of the two sites of every 2-site op."""
     centre = None
     two_q = []
     for kind, site, fa, fb, direction, coeff in plan.ops():
@@ -64,9 +57,35 @@ def test_plan_counts_and_schedule_invariants(qk, n, r, d, n2q):
             centre = site - 1
         else:
             assert kind in (0, 1, 2)
-    # the 2-qubit ops are the circuit's, in the circuit's order
+    return two_q
+
+
+@pytest.mark.parametrize("n,r,d,n2q", [(10, 2, 1, 18), (50, 2, 2, 386), (100, 2, 2, 786), (165, 4, 4, 10360)])
+def test_plan_counts_and_schedule_invariants(qk, n, r, d, n2q):
+    # literal order: the circuit's 2-qubit ops in the circuit's order, gauge moves in between
+    plan, gates = _plan(qk, n, r, 0.5, d, flags=qk.QK_PLAN_LITERAL_ORDER)
+    info = plan.info()
+    assert info.n_qubits == n and info.n_gates == len(gates)
+    assert info.n_ops_2q == n2q
+    assert info.n_ops_1q == n * (r + 1)
+    assert info.n_ops == info.n_ops_2q + info.n_ops_1q + info.n_moves
+    assert info.n_moves > 0
+    two_q = _replay(plan)
     ref = [(qk.GATE_KIND[nm], q[0]) for nm, q, _ in gates if len(q) == 2]
     assert [(k, s) for k, s, _, _ in two_q] == ref
+    # default: every run of (mutually commuting) XXPhase interactions applied as one sweep -> same
+    # interactions, same routing per interaction, (almost) no gauge moves
+    plan2, _ = _plan(qk, n, r, 0.5, d)
+    info2 = plan2.info()
+    assert (info2.n_ops_2q, info2.n_ops_1q) == (n2q, n * (r + 1))
+    assert info2.n_moves <= r
+    two_q2 = _replay(plan2)
+    assert sorted(two_q2) == sorted(two_q)
+    xx = lambda ops: sorted((fa, fb) for k, s, fa, fb in ops if k == 3)   # noqa: E731
+    assert xx(two_q2) == xx(two_q)
+    # 1-qubit layers still separate the repetitions: the k-th Rz layer sees the same interactions before it
+    kinds = [k for k, *_ in plan2.ops()]
+    assert kinds.count(1) == n * r and kinds.count(0) == n
 
 
 def test_plan_from_ansatz_equals_plan_from_gates(qk):

@@ -21,8 +21,8 @@ def _ansatz(n, r, g, d):
     return KernelStateAnsatz(n, r, g, oracle.entanglement_graph(n, d))
 
 
-def _plan(qk, ans, mode, cap, err=1e-16):
-    return qk.Plan(ans.num_qubits, ans.ansatz_circ.get_commands(), mode, err, cap)
+def _plan(qk, ans, mode, cap, err=1e-16, flags=0):
+    return qk.Plan(ans.num_qubits, ans.ansatz_circ.get_commands(), mode, err, cap, flags)
 
 
 def test_dmma_fragment_layout_and_peak(qk, cuda_device):
@@ -60,7 +60,8 @@ def test_simulation_matches_oracle_and_statevector(qk, cuda_device, n, r, g, d, 
     ans = _ansatz(n, r, g, d)
     X = oracle.synthetic_features(N, n, 1)
     emap = oracle.entanglement_graph(n, d)
-    batch = qk.simulate(_plan(qk, ans, mode, cap), X)
+    # literal gate order = the oracle's order, so that truncation decisions can be compared 1:1
+    batch = qk.simulate(_plan(qk, ans, mode, cap, flags=qk.QK_PLAN_LITERAL_ORDER), X)
     info = batch.info()
     assert not np.any(info["flags"]), info["flags"]
     ref = simulate_batch(n, r, g, emap, X, mode="itensors" if mode == 0 else "pytket")
@@ -83,6 +84,12 @@ def test_simulation_matches_oracle_and_statevector(qk, cuda_device, n, r, g, d, 
     assert np.abs(K - Ksv).max() < TOL
     if mode == 1:
         assert np.allclose(info["fidelity"], [m.fidelity for m in ref], atol=1e-12)
+    # default schedule (commuting interactions reordered into sweeps): same states up to truncation noise
+    b2 = qk.simulate(_plan(qk, ans, mode, cap), X)
+    assert not np.any(b2.info()["flags"])
+    K2, _ = b2.gram_store()
+    assert np.abs(K2 - Ksv).max() < TOL
+    assert np.abs(K2 - K).max() < TOL
 
 
 def test_closed_form_empty_map(qk, cuda_device):
@@ -138,7 +145,7 @@ def test_gram_host_abi(qk, cuda_device):
     assert np.abs(K2 - oracle.statevector_gram(n, r, g, emap, X, Y)).max() < TOL
 
 
-def test_config3_shape_against_oracle(qk, cuda_device):
+def test_config3_shape_against_oracle(qk, cuda_device, monkeypatch):
     """50 qubits, 2 layers, distance 2 (BASELINE config 3 shape) on a sample the oracle finishes in
     seconds: Gram within 1e-8 (observed ~1e-12), bond dimensions within the structural bound."""
     from gpu_backend.kernel_state_ansatz import build_kernel_matrix
@@ -160,8 +167,12 @@ def test_config3_shape_against_oracle(qk, cuda_device):
         assert int(prof["info_x"]["chi"].max()) <= 16
         # ITensors rule through the other entry point: same truncation decisions as the oracle
         from cpu_backend.kernel_state_ansatz import build_kernel_matrix as bkm_cpu
-        K0 = bkm_cpu(SingleComm(), ans, X, info_file="/tmp/qk_c3", truncation_error=1e-16)
         ref0 = simulate_batch(n, r, g, emap, X, mode="itensors")
+        K0 = bkm_cpu(SingleComm(), ans, X, info_file="/tmp/qk_c3", truncation_error=1e-16)
+        assert np.abs(K0 - gram_from_mps(ref0)).max() < TOL
+        monkeypatch.setenv("QK_SCHEDULE", "literal")     # the oracle's gate order: identical bond dimensions
+        K0 = bkm_cpu(SingleComm(), ans, X, info_file="/tmp/qk_c3", truncation_error=1e-16)
+        monkeypatch.delenv("QK_SCHEDULE")
         assert np.array_equal(np.array([[1] + m.bond_dims() + [1] for m in ref0]), bkm_cpu.last_profile["info_x"]["chi"])
         assert np.abs(K0 - gram_from_mps(ref0)).max() < 1e-10
 

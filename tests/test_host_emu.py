@@ -26,7 +26,8 @@ def test_emu_matches_oracle_itensors(emu, n, r, g, d, cap):
     X = oracle.synthetic_features(N, n, 0)
     emap = oracle.entanglement_graph(n, d)
     gates = oracle.ansatz_gate_list(n, r, g, emap)
-    states, chi, stats, _ = emu_simulate(emu, n, gates, X, trunc_mode=0, chi_cap=cap)
+    # literal gate order (flags=1) = the oracle's order: truncation decisions comparable 1:1
+    states, chi, stats, _ = emu_simulate(emu, n, gates, X, trunc_mode=0, chi_cap=cap, flags=1)
     ref = simulate_batch(n, r, g, emap, X)
     assert np.array_equal(chi, np.array([[1] + m.bond_dims() + [1] for m in ref]))
     assert not stats[:, 2].any()
@@ -36,6 +37,10 @@ def test_emu_matches_oracle_itensors(emu, n, r, g, d, cap):
     assert np.abs(gram_from_mps(ms) - gram_from_mps(ref)).max() < 1e-11
     if n <= 12:
         assert np.abs(gram_from_mps(ms) - oracle.statevector_gram(n, r, g, emap, X)).max() < 1e-8
+    # default schedule: runs of commuting interactions applied as sweeps, no gauge moves
+    states2, chi2, stats2, (n_ops, n_moves) = emu_simulate(emu, n, gates, X, trunc_mode=0, chi_cap=cap)
+    assert n_moves <= r and not stats2[:, 2].any()
+    assert np.abs(gram_from_mps([TensorsMPS(s) for s in states2]) - gram_from_mps(ref)).max() < 1e-9
 
 
 def test_emu_pytket_mode_and_fidelity(emu):
@@ -70,7 +75,7 @@ def test_emu_group_sizes_agree(emu):
 
 def test_emu_cap_hit_is_flagged(emu):
     n, r, g, d = 10, 2, 1.0, 2
-    X = oracle.synthetic_features(3, n, 0)
+    X = oracle.synthetic_features(6, n, 2)
     gates = oracle.ansatz_gate_list(n, r, g, oracle.entanglement_graph(n, d))
     _, chi, stats, _ = emu_simulate(emu, n, gates, X, chi_cap=4)
     assert chi.max() <= 4
@@ -103,11 +108,11 @@ def test_emu_against_golden(emu):
         n, r, d, g = int(z["n"]), int(z["r"]), int(z["d"]), float(z["gamma"])
         gates = oracle.ansatz_gate_list(n, r, g, oracle.entanglement_graph(n, d))
         cap = 32 if z["chi_X"].max() > 16 else 16
-        sx, chi, _, _ = emu_simulate(emu, n, gates, z["X"], chi_cap=cap)
+        sx, chi, _, _ = emu_simulate(emu, n, gates, z["X"], chi_cap=cap, flags=1)
         assert np.array_equal(chi, z["chi_X"]), f.name
         mx = [TensorsMPS(s) for s in sx]
         if "Y" in z.files:
-            sy, _, _, _ = emu_simulate(emu, n, gates, z["Y"], chi_cap=cap)
+            sy, _, _, _ = emu_simulate(emu, n, gates, z["Y"], chi_cap=cap, flags=1)
             K = gram_from_mps(mx, [TensorsMPS(s) for s in sy])
         else:
             K = gram_from_mps(mx)
