@@ -411,7 +411,11 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-budget", type=float, default=14.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--points", type=int, default=0, help="override the number of datapoints (experiments only)")
     args = ap.parse_args()
+    if args.points > 0:
+        n, r, d, g, _ = WORKLOADS[args.workload]
+        WORKLOADS[args.workload] = (n, r, d, g, args.points)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -10,7 +10,7 @@
 // layout of the next when the contraction index is taken in the order (even columns, odd columns),
 // so the site tensors are stored in HBM already permuted into A-fragment order ("frag" layout,
 // written by qk_pack_kernel) and arrive in shared memory through a 3-stage cp.async.bulk (TMA)
-// + mbarrier pipeline fed by a dedicated producer warp.
+// + mbarrier pipeline issued by one elected lane NS-1 sites ahead of the compute.
 //   * every bond index is stored permuted inside its group of 8 (logical 8t+4e+j <-> physical
 //     8t+2j+e) so that the even / odd k-blocks of a tile hold logical indices 8t..8t+3 / 8t+4..8t+7:
 //     a state whose bond dimension is <= 8t+4 skips the odd k-block (contraction granularity 4).
@@ -19,11 +19,18 @@
 // qk_gram_store_kernel -- CUDA-core FP64 cross-check on the unpadded stores (any chi); used by
 // tests and as the path for bond dimensions above 16.
 #include <stdint.h>
+#include <stdlib.h>
 #include "qk_kernels.cuh"
 
+#ifndef QK_TI
 #define QK_TI 4
+#endif
+#ifndef QK_TJ
 #define QK_TJ 2
+#endif
+#ifndef QK_NS
 #define QK_NS 3
+#endif
 #define QK_GRAM_WARPS (QK_TI * QK_TJ)
 
 void qk_gram_dmma_tile_shape(int* ti, int* tj) { *ti = QK_TI; *tj = QK_TJ; }
@@ -135,7 +142,7 @@ __device__ __forceinline__ void qk_dmma(double (&acc)[2], double a, double b) {
 // DMMA Gram kernel.  NT = max 8x8 tiles per bond (1: D <= 8, 2: D <= 16).
 // ------------------------------------------------------------------------------------------------
 template <int NT>
-__global__ void __launch_bounds__((QK_GRAM_WARPS + 1) * 32, 1) qk_gram_dmma_kernel(const __grid_constant__ GramParams P) {
+__global__ void __launch_bounds__(QK_GRAM_WARPS * 32, 1) qk_gram_dmma_kernel(const __grid_constant__ GramParams P) {
   extern __shared__ __align__(128) unsigned char gsm[];
   const int n = P.n;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -150,7 +157,7 @@ __global__ void __launch_bounds__((QK_GRAM_WARPS + 1) * 32, 1) qk_gram_dmma_kern
   const int y0 = tile.x, x0 = tile.y, y_end = tile.z, x_end = tile.w;
 
   for (int b = threadIdx.x; b <= n; b += blockDim.x) { sDx[b] = P.Dx[b]; sDy[b] = P.Dy[b]; }
-  for (int t = warp; t < QK_TI + QK_TJ; t += QK_GRAM_WARPS + 1) {
+  for (int t = warp; t < QK_TI + QK_TJ; t += QK_GRAM_WARPS) {
     const bool is_x = t < QK_TI;
     int idx = is_x ? x0 + t : y0 + (t - QK_TI);
     const int lim = is_x ? P.Nx : P.Ny;
@@ -167,33 +174,33 @@ __global__ void __launch_bounds__((QK_GRAM_WARPS + 1) * 32, 1) qk_gram_dmma_kern
   }
   __syncthreads();
 
-  if (warp == QK_GRAM_WARPS) {
-    // ===== producer warp: one lane streams the site blocks of the tile's TI kets and TJ bras =====
-    if (lane == 0) {
-      for (int s = 0; s < n; ++s) {
-        const int st = s % QK_NS;
-        const uint32_t par = (uint32_t)((s / QK_NS) & 1);
-        qk_mbar_wait(qk_smem_u32(&bars[QK_NS + st]), par ^ 1u);
-        const uint32_t bx = (uint32_t)(sDx[s] * sDx[s + 1] * 32);
-        const uint32_t by = (uint32_t)(sDy[s] * sDy[s + 1] * 32);
-        const uint32_t full = qk_smem_u32(&bars[st]);
-        qk_mbar_expect_tx(full, QK_TI * bx + QK_TJ * by);
-        unsigned char* dst = stage0 + (size_t)st * stage_bytes;
-        const int64_t ox = P.offx[s], oy = P.offy[s];
+  // The site blocks of the tile's TI kets and TJ bras are streamed by one elected lane (warp 0, lane 0)
+  // NS-1 sites ahead of the compute; a dedicated producer warp would put 3 warps on one scheduler and
+  // cap every thread at 168 registers (16 K registers per scheduler), which the 3M accumulators exceed.
+  auto issue_site = [&](int sl) {
+    const int st = sl % QK_NS;
+    const uint32_t par = (uint32_t)((sl / QK_NS) & 1);
+    qk_mbar_wait(qk_smem_u32(&bars[QK_NS + st]), par ^ 1u);     // all warps released the previous use
+    const uint32_t bxb = (uint32_t)(sDx[sl] * sDx[sl + 1] * 32);
+    const uint32_t byb = (uint32_t)(sDy[sl] * sDy[sl + 1] * 32);
+    const uint32_t full = qk_smem_u32(&bars[st]);
+    qk_mbar_expect_tx(full, QK_TI * bxb + QK_TJ * byb);
+    unsigned char* dst = stage0 + (size_t)st * stage_bytes;
+    const int64_t ox = P.offx[sl], oy = P.offy[sl];
 #pragma unroll
-        for (int t = 0; t < QK_TI; ++t) {
-          int xi = x0 + t; if (xi >= P.Nx) xi = P.Nx - 1;
-          qk_bulk_g2s(qk_smem_u32(dst + (size_t)t * P.slot_x), P.fragX + (size_t)xi * P.strideX + ox, bx, full);
-        }
-#pragma unroll
-        for (int t = 0; t < QK_TJ; ++t) {
-          int yi = y0 + t; if (yi >= P.Ny) yi = P.Ny - 1;
-          qk_bulk_g2s(qk_smem_u32(dst + (size_t)QK_TI * P.slot_x + (size_t)t * P.slot_y),
-                      P.fragY + (size_t)yi * P.strideY + oy, by, full);
-        }
-      }
+    for (int t = 0; t < QK_TI; ++t) {
+      int xi = x0 + t; if (xi >= P.Nx) xi = P.Nx - 1;
+      qk_bulk_g2s(qk_smem_u32(dst + (size_t)t * P.slot_x), P.fragX + (size_t)xi * P.strideX + ox, bxb, full);
     }
-    return;
+#pragma unroll
+    for (int t = 0; t < QK_TJ; ++t) {
+      int yi = y0 + t; if (yi >= P.Ny) yi = P.Ny - 1;
+      qk_bulk_g2s(qk_smem_u32(dst + (size_t)QK_TI * P.slot_x + (size_t)t * P.slot_y),
+                  P.fragY + (size_t)yi * P.strideY + oy, byb, full);
+    }
+  };
+  if (threadIdx.x == 0) {
+    for (int sl = 0; sl < QK_NS - 1 && sl < n; ++sl) issue_site(sl);
   }
 
   // ===== consumer warps: one (bra y, ket x) pair each =====
@@ -216,6 +223,8 @@ __global__ void __launch_bounds__((QK_GRAM_WARPS + 1) * 32, 1) qk_gram_dmma_kern
   for (int s = 0; s < n; ++s) {
     const int st = s % QK_NS;
     const uint32_t par = (uint32_t)((s / QK_NS) & 1);
+    if (threadIdx.x == 0 && s + QK_NS - 1 < n) issue_site(s + QK_NS - 1);
+    __syncwarp();
     qk_mbar_wait(qk_smem_u32(&bars[st]), par);
     if (active) {
       const int KTx = sDx[s] >> 3, MTx = sDx[s + 1] >> 3;
@@ -243,27 +252,38 @@ __global__ void __launch_bounds__((QK_GRAM_WARPS + 1) * 32, 1) qk_gram_dmma_kern
           for (int b = 0; b < NT; ++b) {
             T1[a][b][0] = T1[a][b][1] = 0.0; T2[a][b][0] = T2[a][b][1] = 0.0; T3[a][b][0] = T3[a][b][1] = 0.0;
           }
-        // step 1: T^T[c'][a] += sum_c A_x[c,p,c'] * E[a][c]
+        // fragments of the ket site tensor for this p: loaded up front (always in bounds of the padded
+        // block) so that the shared-memory latency overlaps the MMAs instead of stalling their operands
+        double2 xr[NT][NT], xi[NT][NT];
 #pragma unroll
-        for (int mt = 0; mt < NT; ++mt) {
-          if (mt < mx) {
+        for (int mt = 0; mt < NT; ++mt)
 #pragma unroll
-            for (int kt = 0; kt < NT; ++kt) {
-              if (2 * kt < kbx) {
-                const int fi = (((p * MTx + mt) * KTx + kt) * 2) * 32 + lane;
-                const double2 mr = bx[fi], mi = bx[fi + 32];
-                const double s0 = mr.x + mi.x, s1 = mr.y + mi.y;
-                const bool odd = (2 * kt + 1 < kbx);
+          for (int kt = 0; kt < NT; ++kt) {
+            const int mtc = mt < MTx ? mt : MTx - 1, ktc = kt < KTx ? kt : KTx - 1;
+            const int fi = (((p * MTx + mtc) * KTx + ktc) * 2) * 32 + lane;
+            xr[mt][kt] = bx[fi];
+            xi[mt][kt] = bx[fi + 32];
+          }
+        // step 1: T^T[c'][a] += sum_c A_x[c,p,c'] * E[a][c].  Loop order (k-block outermost) puts 3*mx*ky
+        // independent accumulators between two MMAs on the same one: the DMMA accumulate latency is
+        // longer than three issue slots, so a (tile-inner) order stalls on every odd k-block.
 #pragma unroll
-                for (int at = 0; at < NT; ++at) {
-                  if (at < ky) {
-                    qk_dmma(T1[mt][at], mr.x, Er[at][kt][0]);
-                    qk_dmma(T2[mt][at], mi.x, Ei[at][kt][0]);
-                    qk_dmma(T3[mt][at], s0, Es[at][kt][0]);
-                    if (odd) {
-                      qk_dmma(T1[mt][at], mr.y, Er[at][kt][1]);
-                      qk_dmma(T2[mt][at], mi.y, Ei[at][kt][1]);
-                      qk_dmma(T3[mt][at], s1, Es[at][kt][1]);
+        for (int kt = 0; kt < NT; ++kt) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            if (2 * kt + e < kbx) {
+#pragma unroll
+              for (int mt = 0; mt < NT; ++mt) {
+                if (mt < mx) {
+                  const double ar = e ? xr[mt][kt].y : xr[mt][kt].x;
+                  const double ai = e ? xi[mt][kt].y : xi[mt][kt].x;
+                  const double as = ar + ai;
+#pragma unroll
+                  for (int at = 0; at < NT; ++at) {
+                    if (at < ky) {
+                      qk_dmma(T1[mt][at], ar, Er[at][kt][e]);
+                      qk_dmma(T2[mt][at], ai, Ei[at][kt][e]);
+                      qk_dmma(T3[mt][at], as, Es[at][kt][e]);
                     }
                   }
                 }
@@ -271,6 +291,17 @@ __global__ void __launch_bounds__((QK_GRAM_WARPS + 1) * 32, 1) qk_gram_dmma_kern
             }
           }
         }
+        // bra fragments for step 2 (issued before the combine so the two overlap)
+        double2 yr[NT][NT], yi[NT][NT];
+#pragma unroll
+        for (int bt = 0; bt < NT; ++bt)
+#pragma unroll
+          for (int at = 0; at < NT; ++at) {
+            const int btc = bt < MTy ? bt : MTy - 1, atc = at < KTy ? at : KTy - 1;
+            const int fi = (((p * MTy + btc) * KTy + atc) * 2) * 32 + lane;
+            yr[bt][at] = by[fi];
+            yi[bt][at] = by[fi + 32];
+          }
         // T = (S1 - S2) + i (S3 - S1 - S2);  reuse T1 = Tr, T2 = Ti, T3 = Tr + Ti
 #pragma unroll
         for (int a = 0; a < NT; ++a)
@@ -285,25 +316,22 @@ __global__ void __launch_bounds__((QK_GRAM_WARPS + 1) * 32, 1) qk_gram_dmma_kern
             }
         // step 2: E'[b'][c'] += sum_a conj(A_y[a,p,b']) * T[a][c']:  S1 = Ar Tr, S2 = Ai Ti, S3 = (Ar-Ai)(Tr+Ti)
 #pragma unroll
-        for (int bt = 0; bt < NT; ++bt) {
-          if (bt < my) {
+        for (int at = 0; at < NT; ++at) {
 #pragma unroll
-            for (int at = 0; at < NT; ++at) {
-              if (2 * at < kby) {
-                const int fi = (((p * MTy + bt) * KTy + at) * 2) * 32 + lane;
-                const double2 mr = by[fi], mi = by[fi + 32];
-                const double d0 = mr.x - mi.x, d1 = mr.y - mi.y;
-                const bool odd = (2 * at + 1 < kby);
+          for (int e = 0; e < 2; ++e) {
+            if (2 * at + e < kby) {
 #pragma unroll
-                for (int ct = 0; ct < NT; ++ct) {
-                  if (ct < mx) {
-                    qk_dmma(F1[bt][ct], mr.x, T1[ct][at][0]);
-                    qk_dmma(F2[bt][ct], mi.x, T2[ct][at][0]);
-                    qk_dmma(F3[bt][ct], d0, T3[ct][at][0]);
-                    if (odd) {
-                      qk_dmma(F1[bt][ct], mr.y, T1[ct][at][1]);
-                      qk_dmma(F2[bt][ct], mi.y, T2[ct][at][1]);
-                      qk_dmma(F3[bt][ct], d1, T3[ct][at][1]);
+              for (int bt = 0; bt < NT; ++bt) {
+                if (bt < my) {
+                  const double ar = e ? yr[bt][at].y : yr[bt][at].x;
+                  const double ai = e ? yi[bt][at].y : yi[bt][at].x;
+                  const double ad = ar - ai;
+#pragma unroll
+                  for (int ct = 0; ct < NT; ++ct) {
+                    if (ct < mx) {
+                      qk_dmma(F1[bt][ct], ar, T1[ct][at][e]);
+                      qk_dmma(F2[bt][ct], ai, T2[ct][at][e]);
+                      qk_dmma(F3[bt][ct], ad, T3[ct][at][e]);
                     }
                   }
                 }
@@ -348,7 +376,7 @@ static cudaError_t launch_gram_nt(const GramParams& P, cudaStream_t stream) {
   const size_t smem = gram_smem_bytes(P);
   cudaError_t e = cudaFuncSetAttribute(qk_gram_dmma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  qk_gram_dmma_kernel<NT><<<P.n_cta_tiles, (QK_GRAM_WARPS + 1) * 32, smem, stream>>>(P);
+  qk_gram_dmma_kernel<NT><<<P.n_cta_tiles, QK_GRAM_WARPS * 32, smem, stream>>>(P);
   return cudaGetLastError();
 }
 
@@ -442,7 +470,12 @@ cudaError_t qk_run_dmma_peak(int iters, double* tflops) {
   double* sink = nullptr;
   cudaError_t e = cudaMalloc(&sink, sizeof(double));
   if (e != cudaSuccess) return e;
-  const int grid = sms * 4, block = 256;
+  int grid = sms * 4, block = 256;
+  if (const char* e = getenv("QK_PEAK_WARPS_PER_SM")) {   // experiments: DMMA rate at a given occupancy
+    const int w = atoi(e);
+    if (w >= 1 && w <= 8) { grid = sms; block = 32 * w; }
+    else if (w > 8 && w <= 64) { grid = sms * (w / 8); block = 256; }
+  }
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   qk_dmma_peak_kernel<<<grid, block>>>(iters / 8 + 1, sink);   // warm-up

@@ -149,8 +149,19 @@ def build_gram(comm, plan_factory, n_qubits, X, Y=None, chi_cap=16, device=None,
     Dx = pad_dims(allreduce_max_array(comm, bx.max_chi()))
     Dy = Dx if symmetric else pad_dims(allreduce_max_array(comm, by.max_chi()))
     if int(max(Dx.max(), Dy.max())) > DMMA_D_LIMIT:
-        raise QkError(-3, f"padded bond dimension {int(max(Dx.max(), Dy.max()))} above the tensor-core overlap "
-                          f"kernel's limit ({DMMA_D_LIMIT}); use Batch.gram_store for such states")
+        # bond dimensions above the register-resident tensor-core kernel (D <= 16): CUDA-core FP64 kernel on
+        # the unpadded stores.  It needs both batches on one device, so it is single-rank only for now.
+        if size > 1:
+            raise QkError(-3, f"padded bond dimension {int(max(Dx.max(), Dy.max()))} above the tensor-core overlap "
+                              f"kernel's limit ({DMMA_D_LIMIT}) is only supported on one rank")
+        Kh, ms = bx.gram_store(by)
+        if symmetric:
+            Kh = 0.5 * (Kh + Kh.T)     # <y|x> and <x|y> are computed independently: symmetrise the rounding
+        prof.update(gram_ms=ms, Dx=Dx, Dy=Dy, launches=launches + 1, exchange_s=time.perf_counter() - t0,
+                    frag_bytes_per_state=(0, 0), gram_kernel="qk_gram_store_kernel", no_converge=0)
+        out = torch.from_numpy(Kh).to(dev) if return_device else Kh
+        prof["total_s"] = time.perf_counter() - t_all
+        return out, prof
     stream = torch.cuda.current_stream().cuda_stream
 
     def packed(batch, D, n_total):

@@ -1,0 +1,3 @@
+for w in 4 8 16 32; do QK_PEAK_WARPS_PER_SM=$w python -c "
+import sys; sys.path.insert(0,'qml-cutensornet_b200')
+import qkmps; print('warps/SM', $w, 'DMMA TFLOP/s', round(qkmps.dmma_peak(0, 40000),2))"; done
