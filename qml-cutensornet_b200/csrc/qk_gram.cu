@@ -139,6 +139,138 @@ __device__ __forceinline__ void qk_dmma(double (&acc)[2], double a, double b) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// One site of the transfer sweep for one (bra, ket) pair, E kept in accumulator fragments.
+//   STATIC = true : every 8-tile of the four bonds involved is live and the live k-block counts are
+//                   the compile-time KBX / KBY -> straight-line code, no predicate around any MMA.
+//                   (ptxas paces DMMAs with static stall counts and guards every predicated
+//                   mma.sync with WARPSYNC + NOPs, so a predicated-off MMA costs as much as a real one.)
+//   STATIC = false: generic path, live tiles / k-blocks from the per-state trailer bytes.
+// ------------------------------------------------------------------------------------------------
+template <int NT, bool STATIC, int KBX, int KBY>
+__device__ __forceinline__ void qk_site_step(double (&Er)[NT][NT][2], double (&Ei)[NT][NT][2], double (&Es)[NT][NT][2],
+                                             const double2* __restrict__ bx, const double2* __restrict__ by, int lane,
+                                             int MTx_r, int KTx_r, int MTy_r, int KTy_r, int mx_r, int my_r, int ky_r,
+                                             int kbx_r, int kby_r) {
+  const int MTx = STATIC ? NT : MTx_r, KTx = STATIC ? NT : KTx_r, MTy = STATIC ? NT : MTy_r, KTy = STATIC ? NT : KTy_r;
+  const int mx = STATIC ? NT : mx_r, my = STATIC ? NT : my_r, ky = STATIC ? NT : ky_r;
+  const int kbx = STATIC ? KBX : kbx_r, kby = STATIC ? KBY : kby_r;
+  double F1[NT][NT][2], F2[NT][NT][2], F3[NT][NT][2];   // E' as S1, S2, S3 over both p
+#pragma unroll
+  for (int a = 0; a < NT; ++a)
+#pragma unroll
+    for (int b = 0; b < NT; ++b) {
+      F1[a][b][0] = F1[a][b][1] = 0.0; F2[a][b][0] = F2[a][b][1] = 0.0; F3[a][b][0] = F3[a][b][1] = 0.0;
+    }
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    // T^T[ket-right tile][bra-left tile] as S1 = Ar Er, S2 = Ai Ei, S3 = (Ar+Ai)(Er+Ei)
+    double T1[NT][NT][2], T2[NT][NT][2], T3[NT][NT][2];
+#pragma unroll
+    for (int a = 0; a < NT; ++a)
+#pragma unroll
+      for (int b = 0; b < NT; ++b) {
+        T1[a][b][0] = T1[a][b][1] = 0.0; T2[a][b][0] = T2[a][b][1] = 0.0; T3[a][b][0] = T3[a][b][1] = 0.0;
+      }
+    // fragments of the ket site tensor for this p: loaded up front (always in bounds of the padded block)
+    double2 xr[NT][NT], xi[NT][NT];
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+      for (int kt = 0; kt < NT; ++kt) {
+        const int mtc = mt < MTx ? mt : MTx - 1, ktc = kt < KTx ? kt : KTx - 1;
+        const int fi = (((p * MTx + mtc) * KTx + ktc) * 2) * 32 + lane;
+        xr[mt][kt] = bx[fi];
+        xi[mt][kt] = bx[fi + 32];
+      }
+    // step 1: T^T[c'][a] += sum_c A_x[c,p,c'] * E[a][c]   (k-block outermost: 3*mx*ky independent accumulators)
+#pragma unroll
+    for (int kt = 0; kt < NT; ++kt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (2 * kt + e < kbx) {
+#pragma unroll
+          for (int mt = 0; mt < NT; ++mt) {
+            if (mt < mx) {
+              const double ar = e ? xr[mt][kt].y : xr[mt][kt].x;
+              const double ai = e ? xi[mt][kt].y : xi[mt][kt].x;
+              const double as = ar + ai;
+#pragma unroll
+              for (int at = 0; at < NT; ++at) {
+                if (at < ky) {
+                  qk_dmma(T1[mt][at], ar, Er[at][kt][e]);
+                  qk_dmma(T2[mt][at], ai, Ei[at][kt][e]);
+                  qk_dmma(T3[mt][at], as, Es[at][kt][e]);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    // bra fragments for step 2 (issued before the combine so the two overlap)
+    double2 yr[NT][NT], yi[NT][NT];
+#pragma unroll
+    for (int bt = 0; bt < NT; ++bt)
+#pragma unroll
+      for (int at = 0; at < NT; ++at) {
+        const int btc = bt < MTy ? bt : MTy - 1, atc = at < KTy ? at : KTy - 1;
+        const int fi = (((p * MTy + btc) * KTy + atc) * 2) * 32 + lane;
+        yr[bt][at] = by[fi];
+        yi[bt][at] = by[fi + 32];
+      }
+    // T = (S1 - S2) + i (S3 - S1 - S2);  reuse T1 = Tr, T2 = Ti, T3 = Tr + Ti
+#pragma unroll
+    for (int a = 0; a < NT; ++a)
+#pragma unroll
+      for (int b = 0; b < NT; ++b)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const double u1 = T1[a][b][e], u2 = T2[a][b][e], u3 = T3[a][b][e];
+          T1[a][b][e] = u1 - u2;
+          T2[a][b][e] = u3 - u1 - u2;
+          T3[a][b][e] = u3 - 2.0 * u2;
+        }
+    // step 2: E'[b'][c'] += sum_a conj(A_y[a,p,b']) * T[a][c']:  S1 = Ar Tr, S2 = Ai Ti, S3 = (Ar-Ai)(Tr+Ti)
+#pragma unroll
+    for (int at = 0; at < NT; ++at) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (2 * at + e < kby) {
+#pragma unroll
+          for (int bt = 0; bt < NT; ++bt) {
+            if (bt < my) {
+              const double ar = e ? yr[bt][at].y : yr[bt][at].x;
+              const double ai = e ? yi[bt][at].y : yi[bt][at].x;
+              const double ad = ar - ai;
+#pragma unroll
+              for (int ct = 0; ct < NT; ++ct) {
+                if (ct < mx) {
+                  qk_dmma(F1[bt][ct], ar, T1[ct][at][e]);
+                  qk_dmma(F2[bt][ct], ai, T2[ct][at][e]);
+                  qk_dmma(F3[bt][ct], ad, T3[ct][at][e]);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  // E' = (S1 + S2) + i (S3 - S1 + S2)
+#pragma unroll
+  for (int a = 0; a < NT; ++a)
+#pragma unroll
+    for (int b = 0; b < NT; ++b)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const double u1 = F1[a][b][e], u2 = F2[a][b][e], u3 = F3[a][b][e];
+        Er[a][b][e] = u1 + u2;
+        Ei[a][b][e] = u3 - u1 + u2;
+        Es[a][b][e] = u3 + 2.0 * u2;
+      }
+}
+
+// ------------------------------------------------------------------------------------------------
 // DMMA Gram kernel.  NT = max 8x8 tiles per bond (1: D <= 8, 2: D <= 16).
 // ------------------------------------------------------------------------------------------------
 template <int NT>
@@ -167,8 +299,8 @@ __global__ void __launch_bounds__(QK_GRAM_WARPS * 32, 1) qk_gram_dmma_kernel(con
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < QK_NS; ++s) {
-      qk_mbar_init(qk_smem_u32(&bars[s]), 1);                       // full: producer's expect_tx arrive
-      qk_mbar_init(qk_smem_u32(&bars[QK_NS + s]), QK_GRAM_WARPS);   // empty: one arrive per consumer warp
+      qk_mbar_init(qk_smem_u32(&bars[s]), 1);                       // full: the issuing lane's expect_tx arrive
+      qk_mbar_init(qk_smem_u32(&bars[QK_NS + s]), QK_GRAM_WARPS);   // empty: one arrive per warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -203,7 +335,7 @@ __global__ void __launch_bounds__(QK_GRAM_WARPS * 32, 1) qk_gram_dmma_kernel(con
     for (int sl = 0; sl < QK_NS - 1 && sl < n; ++sl) issue_site(sl);
   }
 
-  // ===== consumer warps: one (bra y, ket x) pair each =====
+  // ===== one (bra y, ket x) pair per warp =====
   const int ti = warp % QK_TI, tj = warp / QK_TI;
   const int x = x0 + ti, y = y0 + tj;
   const bool active = (x < x_end) && (y < y_end) && (!P.symmetric || x <= y);
@@ -235,123 +367,20 @@ __global__ void __launch_bounds__(QK_GRAM_WARPS * 32, 1) qk_gram_dmma_kernel(con
       const unsigned char* sb = stage0 + (size_t)st * stage_bytes;
       const double2* bx = (const double2*)(sb + (size_t)ti * P.slot_x);
       const double2* by = (const double2*)(sb + (size_t)QK_TI * P.slot_x + (size_t)tj * P.slot_y);
-      double F1[NT][NT][2], F2[NT][NT][2], F3[NT][NT][2];   // E' as S1, S2, S3 over both p
-#pragma unroll
-      for (int a = 0; a < NT; ++a)
-#pragma unroll
-        for (int b = 0; b < NT; ++b) {
-          F1[a][b][0] = F1[a][b][1] = 0.0; F2[a][b][0] = F2[a][b][1] = 0.0; F3[a][b][0] = F3[a][b][1] = 0.0;
+      // common case in the bulk of the chain: all tiles live, k-block counts 2NT or 2NT-1
+      const bool full = (mx == NT) && (my == NT) && (kbx >= 2 * NT - 1) && (kby >= 2 * NT - 1) &&
+                        (MTx == NT) && (KTx == NT) && (MTy == NT) && (KTy == NT);
+      if (full) {
+        if (kbx == 2 * NT) {
+          if (kby == 2 * NT) qk_site_step<NT, true, 2 * NT, 2 * NT>(Er, Ei, Es, bx, by, lane, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+          else qk_site_step<NT, true, 2 * NT, 2 * NT - 1>(Er, Ei, Es, bx, by, lane, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+        } else {
+          if (kby == 2 * NT) qk_site_step<NT, true, 2 * NT - 1, 2 * NT>(Er, Ei, Es, bx, by, lane, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+          else qk_site_step<NT, true, 2 * NT - 1, 2 * NT - 1>(Er, Ei, Es, bx, by, lane, 0, 0, 0, 0, 0, 0, 0, 0, 0);
         }
-#pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        // T^T[ket-right tile][bra-left tile] as S1 = Ar Er, S2 = Ai Ei, S3 = (Ar+Ai)(Er+Ei)
-        double T1[NT][NT][2], T2[NT][NT][2], T3[NT][NT][2];
-#pragma unroll
-        for (int a = 0; a < NT; ++a)
-#pragma unroll
-          for (int b = 0; b < NT; ++b) {
-            T1[a][b][0] = T1[a][b][1] = 0.0; T2[a][b][0] = T2[a][b][1] = 0.0; T3[a][b][0] = T3[a][b][1] = 0.0;
-          }
-        // fragments of the ket site tensor for this p: loaded up front (always in bounds of the padded
-        // block) so that the shared-memory latency overlaps the MMAs instead of stalling their operands
-        double2 xr[NT][NT], xi[NT][NT];
-#pragma unroll
-        for (int mt = 0; mt < NT; ++mt)
-#pragma unroll
-          for (int kt = 0; kt < NT; ++kt) {
-            const int mtc = mt < MTx ? mt : MTx - 1, ktc = kt < KTx ? kt : KTx - 1;
-            const int fi = (((p * MTx + mtc) * KTx + ktc) * 2) * 32 + lane;
-            xr[mt][kt] = bx[fi];
-            xi[mt][kt] = bx[fi + 32];
-          }
-        // step 1: T^T[c'][a] += sum_c A_x[c,p,c'] * E[a][c].  Loop order (k-block outermost) puts 3*mx*ky
-        // independent accumulators between two MMAs on the same one: the DMMA accumulate latency is
-        // longer than three issue slots, so a (tile-inner) order stalls on every odd k-block.
-#pragma unroll
-        for (int kt = 0; kt < NT; ++kt) {
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            if (2 * kt + e < kbx) {
-#pragma unroll
-              for (int mt = 0; mt < NT; ++mt) {
-                if (mt < mx) {
-                  const double ar = e ? xr[mt][kt].y : xr[mt][kt].x;
-                  const double ai = e ? xi[mt][kt].y : xi[mt][kt].x;
-                  const double as = ar + ai;
-#pragma unroll
-                  for (int at = 0; at < NT; ++at) {
-                    if (at < ky) {
-                      qk_dmma(T1[mt][at], ar, Er[at][kt][e]);
-                      qk_dmma(T2[mt][at], ai, Ei[at][kt][e]);
-                      qk_dmma(T3[mt][at], as, Es[at][kt][e]);
-                    }
-                  }
-                }
-              }
-            }
-          }
-        }
-        // bra fragments for step 2 (issued before the combine so the two overlap)
-        double2 yr[NT][NT], yi[NT][NT];
-#pragma unroll
-        for (int bt = 0; bt < NT; ++bt)
-#pragma unroll
-          for (int at = 0; at < NT; ++at) {
-            const int btc = bt < MTy ? bt : MTy - 1, atc = at < KTy ? at : KTy - 1;
-            const int fi = (((p * MTy + btc) * KTy + atc) * 2) * 32 + lane;
-            yr[bt][at] = by[fi];
-            yi[bt][at] = by[fi + 32];
-          }
-        // T = (S1 - S2) + i (S3 - S1 - S2);  reuse T1 = Tr, T2 = Ti, T3 = Tr + Ti
-#pragma unroll
-        for (int a = 0; a < NT; ++a)
-#pragma unroll
-          for (int b = 0; b < NT; ++b)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const double u1 = T1[a][b][e], u2 = T2[a][b][e], u3 = T3[a][b][e];
-              T1[a][b][e] = u1 - u2;
-              T2[a][b][e] = u3 - u1 - u2;
-              T3[a][b][e] = u3 - 2.0 * u2;
-            }
-        // step 2: E'[b'][c'] += sum_a conj(A_y[a,p,b']) * T[a][c']:  S1 = Ar Tr, S2 = Ai Ti, S3 = (Ar-Ai)(Tr+Ti)
-#pragma unroll
-        for (int at = 0; at < NT; ++at) {
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            if (2 * at + e < kby) {
-#pragma unroll
-              for (int bt = 0; bt < NT; ++bt) {
-                if (bt < my) {
-                  const double ar = e ? yr[bt][at].y : yr[bt][at].x;
-                  const double ai = e ? yi[bt][at].y : yi[bt][at].x;
-                  const double ad = ar - ai;
-#pragma unroll
-                  for (int ct = 0; ct < NT; ++ct) {
-                    if (ct < mx) {
-                      qk_dmma(F1[bt][ct], ar, T1[ct][at][e]);
-                      qk_dmma(F2[bt][ct], ai, T2[ct][at][e]);
-                      qk_dmma(F3[bt][ct], ad, T3[ct][at][e]);
-                    }
-                  }
-                }
-              }
-            }
-          }
-        }
+      } else {
+        qk_site_step<NT, false, 0, 0>(Er, Ei, Es, bx, by, lane, MTx, KTx, MTy, KTy, mx, my, ky, kbx, kby);
       }
-      // E' = (S1 + S2) + i (S3 - S1 + S2)
-#pragma unroll
-      for (int a = 0; a < NT; ++a)
-#pragma unroll
-        for (int b = 0; b < NT; ++b)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const double u1 = F1[a][b][e], u2 = F2[a][b][e], u3 = F3[a][b][e];
-            Er[a][b][e] = u1 + u2;
-            Ei[a][b][e] = u3 - u1 + u2;
-            Es[a][b][e] = u3 + 2.0 * u2;
-          }
     }
     __syncwarp();
     if (lane == 0) qk_mbar_arrive(qk_smem_u32(&bars[QK_NS + st]));

@@ -10,8 +10,11 @@
 #include "qk_kernels.cuh"
 #include "qk_sim_core.h"
 
+// resident CTAs per SM the register allocation is sized for (shared memory allows 6 at chi_cap 16)
+template <int G> struct SimMinBlocks { static constexpr int value = (G == 128) ? 6 : (G == 64) ? 8 : (G == 32) ? 12 : 2; };
+
 template <int G>
-__global__ void __launch_bounds__(G) qk_sim_kernel(const __grid_constant__ SimParams P, int* work_counter) {
+__global__ void __launch_bounds__(G, SimMinBlocks<G>::value) qk_sim_kernel(const __grid_constant__ SimParams P, int* work_counter) {
   extern __shared__ __align__(16) unsigned char qk_smem[];
   __shared__ int next_dp;
   SimCtx c;

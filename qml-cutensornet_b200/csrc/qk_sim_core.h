@@ -33,6 +33,13 @@
 #ifndef QK_PI
 #define QK_PI 3.14159265358979323846
 #endif
+// reduction scratch doubles per thread: the device reduces the Jacobi dot products with warp shuffles
+// and only needs 2 (Householder); the host emulation stages 4 partial sums per thread
+#if defined(QK_HOST_EMU)
+#define QK_SCR_PER_THREAD 4
+#else
+#define QK_SCR_PER_THREAD 2
+#endif
 
 struct SimShared {
   int rotated;
@@ -67,7 +74,7 @@ struct SimCtx {
 QK_HD size_t qk_sim_smem_bytes(int n, int rmax, int G) {
   size_t wr = (size_t)rmax * rmax;
   size_t b = 2 * wr * sizeof(c128);         // W, J
-  b += (size_t)4 * G * sizeof(double);      // scr
+  b += (size_t)QK_SCR_PER_THREAD * G * sizeof(double);   // scr
   b += (size_t)rmax * sizeof(double);       // nrm2
   b += 16 * sizeof(c128);                   // gate
   b += (size_t)rmax * sizeof(c128);         // diag
@@ -84,7 +91,7 @@ QK_DEV void qk_sim_carve(SimCtx& c, const SimParams* P, unsigned char* smem, int
   c.W = (c128*)smem;
   c.J = c.W + wr;
   c.scr = (double*)(c.J + wr);
-  c.nrm2 = c.scr + 4 * G;
+  c.nrm2 = c.scr + QK_SCR_PER_THREAD * G;
   c.gate = (c128*)(c.nrm2 + P->rmax + (P->rmax & 1));
   c.diag = c.gate + 16;
   c.x = (double*)(c.diag + P->rmax);
@@ -188,12 +195,17 @@ QK_DEV double qk_rcp(double x) {
 // Written with two dependent rsqrt only (the parameter chain is the latency floor of a Jacobi round):
 //   h = sqrt((b-a)^2 + 4|gamma|^2);  cos(2 theta) = |b-a|/h;  sin(2 theta) e^{i phi} = 2 gamma / h;
 //   cos^2(theta) = (1 + cos 2theta)/2;  sin(theta) = sin(2 theta) / (2 cos(theta)).
-QK_DEV bool qk_rotation(double a, double b, double gr, double gi, double tol2, double floor2, double& cs, c128& f) {
+// Return value: 0 = no rotation, 1 = rotation with relative off-diagonal below QK_QUAD_EPS, 2 = above.
+// One-sided Jacobi converges quadratically per sweep, so a sweep whose largest relative off-diagonal
+// was below QK_QUAD_EPS = 1e-9 leaves every pair below ~1e-18 after its own rotations: the usual
+// "empty" verification sweep (a quarter of the work at ~3 sweeps per SVD) is not needed.
+#define QK_QUAD_EPS2 1e-18
+QK_DEV int qk_rotation(double a, double b, double gr, double gi, double tol2, double floor2, double& cs, c128& f) {
   const double g2 = gr * gr + gi * gi;
   // a column whose weight is < 1e-28 of the total is numerically zero (rank-deficient theta is the
   // common case); rotating it again only chases rounding noise
   const bool live = (a > floor2) && (b > floor2);
-  if (!(live && g2 > tol2 * a * b && g2 > 0.0)) return false;
+  if (!(live && g2 > tol2 * a * b && g2 > 0.0)) return 0;
   const double tau = b - a;
   const double rh = qk_rsqrt(fma(tau, tau, 4.0 * g2));
   const double x = fma(0.5 * fabs(tau), rh, 0.5);
@@ -201,7 +213,7 @@ QK_DEV bool qk_rotation(double a, double b, double gr, double gi, double tol2, d
   cs = x * rs;
   const double k = (tau >= 0.0 ? rh : -rh) * rs;
   f = cmake(k * gr, k * gi);
-  return true;
+  return (g2 > QK_QUAD_EPS2 * a * b) ? 2 : 1;
 }
 
 QK_DEV void qk_rot2(c128& xp, c128& xq, double cs, c128 f) {
@@ -247,7 +259,8 @@ __device__ __forceinline__ void qk_pair_step(c128* __restrict__ wp, c128* __rest
     gi += __shfl_xor_sync(0xffffffffu, gi, off);
   }
   double cs; c128 f;
-  if (valid && qk_rotation(a, b, gr, gi, tol2, floor2, cs, f)) {
+  const int rot = valid ? qk_rotation(a, b, gr, gi, tol2, floor2, cs, f) : 0;
+  if (rot) {
 #pragma unroll
     for (int k = 0; k < RPT; ++k) {
       const int row = sl + k * tpp;
@@ -267,7 +280,7 @@ __device__ __forceinline__ void qk_pair_step(c128* __restrict__ wp, c128* __rest
         jq[row] = yq;
       }
     }
-    if (sl == 0) *rotated = 1;
+    if (sl == 0 && rot == 2) *rotated = 1;
   }
 }
 
@@ -291,10 +304,11 @@ __device__ __forceinline__ void qk_pair_step_generic(c128* wp, c128* wq, c128* j
     gi += __shfl_xor_sync(0xffffffffu, gi, off);
   }
   double cs; c128 f;
-  if (valid && qk_rotation(a, b, gr, gi, tol2, floor2, cs, f)) {
+  const int rot = valid ? qk_rotation(a, b, gr, gi, tol2, floor2, cs, f) : 0;
+  if (rot) {
     qk_rotate_rows(wp, wq, R, sl, tpp, cs, f);
     qk_rotate_rows(jp, jq, C, sl, tpp, cs, f);
-    if (sl == 0) *rotated = 1;
+    if (sl == 0 && rot == 2) *rotated = 1;
   }
 }
 #endif
@@ -378,10 +392,11 @@ QK_DEV void qk_jacobi(SimCtx& c, int R, int C) {
                 a += s4[0]; b += s4[1]; gr += s4[2]; gi += s4[3];
               }
               double cs; c128 f;
-              if (qk_rotation(a, b, gr, gi, tol2, floor2, cs, f)) {
+              const int rot = qk_rotation(a, b, gr, gi, tol2, floor2, cs, f);
+              if (rot) {
                 qk_rotate_rows(W + (size_t)p * ldw, W + (size_t)q * ldw, R, sl, tpp, cs, f);
                 qk_rotate_rows(J + (size_t)p * C, J + (size_t)q * C, C, sl, tpp, cs, f);
-                if (sl == 0) c.sh->rotated = 1;
+                if (sl == 0 && rot == 2) c.sh->rotated = 1;
               }
             }
           QK_PAR_END

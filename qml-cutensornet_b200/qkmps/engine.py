@@ -97,7 +97,7 @@ def _simulate_shard(plan_factory, X_shard, device, chi_cap, comm, n_qubits):
         if chi_cap >= CHI_LIMIT:
             raise QkError(-3, f"bond dimension exceeds the shared-memory-resident limit (chi <= {CHI_LIMIT}); "
                               "the large-chi stage-1 path is not implemented")
-        chi_cap = min(2 * chi_cap, CHI_LIMIT)
+        chi_cap = min(max(chi_cap + 1, (chi_cap * 3 // 2 + 3) // 4 * 4), CHI_LIMIT)   # 4 -> 8 -> 12 -> 20 -> 32 ; 16 -> 24 -> 32
 
 
 def build_gram(comm, plan_factory, n_qubits, X, Y=None, chi_cap=16, device=None, return_device=False):
