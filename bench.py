@@ -373,6 +373,16 @@ def run_ours(args):
               "peak_source": hbm_src, "algorithmic_bytes_per_launch": b1,
               "note": "stage 1 is bound by FP64 Jacobi-SVD arithmetic and barrier latency, not HBM: the algorithmic "
                       "byte model of SURVEY.md 8(d) is reported as asked, see DESIGN.md"}
+    # DRAM traffic per launch from the committed ncu captures (valid for the default workload on one GPU)
+    try:
+        tr = json.load(open(ROOT / "profiles" / "r01_dram_traffic.json"))
+        if world == 1 and args.workload == "c3" and args.points == 0:
+            stage1["traffic"] = tr["qk_sim_kernel"]["dram_bytes"]
+            stage2["traffic"] = tr["qk_gram_dmma_kernel"]["dram_bytes"]
+            stage1["traffic_source"] = tr["qk_sim_kernel"]["capture"]
+            stage2["traffic_source"] = tr["qk_gram_dmma_kernel"]["capture"]
+    except Exception:
+        pass
     dominant = stage2 if gram_mean >= sim_mean else stage1
     roofline = {k: dominant[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
     roofline["kernel"] = dominant["kernel"]

@@ -482,6 +482,7 @@ int qk_gram_frags(int device, void* stream_v, int n_qubits, const int32_t* Dx, c
   P.tiles = (const int4*)(dbuf + t_off); P.n_cta_tiles = (int)cta.size();
   P.symmetric = symmetric ? 1 : 0;
   P.K = K_dev; P.ldk = ldk; P.slot_x = slot_x; P.slot_y = slot_y;
+  P.skew_ns = getenv("QK_GRAM_SKEW_NS") ? atoi(getenv("QK_GRAM_SKEW_NS")) : 0;
   if (e == cudaSuccess) e = cudaEventCreate(&e0);
   if (e == cudaSuccess) e = cudaEventCreate(&e1);
   if (e == cudaSuccess) e = cudaEventRecord(e0, stream);

@@ -138,6 +138,12 @@ __device__ __forceinline__ void qk_dmma(double (&acc)[2], double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(acc[0]), "+d"(acc[1]) : "d"(a), "d"(b));
 }
 
+// same with a zero accumulator input (first MMA of a chain: no register zero-fill needed)
+__device__ __forceinline__ void qk_dmma_z(double (&acc)[2], double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+      : "=d"(acc[0]), "=d"(acc[1]) : "d"(a), "d"(b), "d"(0.0), "d"(0.0));
+}
+
 // ------------------------------------------------------------------------------------------------
 // One site of the transfer sweep for one (bra, ket) pair, E kept in accumulator fragments.
 //   STATIC = true : every 8-tile of the four bonds involved is live and the live k-block counts are
@@ -154,52 +160,50 @@ __device__ __forceinline__ void qk_site_step(double (&Er)[NT][NT][2], double (&E
   const int MTx = STATIC ? NT : MTx_r, KTx = STATIC ? NT : KTx_r, MTy = STATIC ? NT : MTy_r, KTy = STATIC ? NT : KTy_r;
   const int mx = STATIC ? NT : mx_r, my = STATIC ? NT : my_r, ky = STATIC ? NT : ky_r;
   const int kbx = STATIC ? KBX : kbx_r, kby = STATIC ? KBY : kby_r;
-  double F1[NT][NT][2], F2[NT][NT][2], F3[NT][NT][2];   // E' as S1, S2, S3 over both p
+  // Both physical indices p are carried together: all step-1 MMAs (p = 0, 1), one combine, all step-2
+  // MMAs, one combine -- two MMA -> DADD -> MMA dependency bubbles per site instead of four, and long
+  // uninterrupted MMA phases that the sibling warp on the scheduler can interleave with.
+  double T1[2][NT][NT][2], T2[2][NT][NT][2], T3[2][NT][NT][2];   // T^T[p][ket-right tile][bra-left tile]
+  if (!STATIC) {   // the static path starts every accumulator chain with a zero-input MMA instead
 #pragma unroll
-  for (int a = 0; a < NT; ++a)
+    for (int p = 0; p < 2; ++p)
 #pragma unroll
-    for (int b = 0; b < NT; ++b) {
-      F1[a][b][0] = F1[a][b][1] = 0.0; F2[a][b][0] = F2[a][b][1] = 0.0; F3[a][b][0] = F3[a][b][1] = 0.0;
-    }
+      for (int a = 0; a < NT; ++a)
 #pragma unroll
-  for (int p = 0; p < 2; ++p) {
-    // T^T[ket-right tile][bra-left tile] as S1 = Ar Er, S2 = Ai Ei, S3 = (Ar+Ai)(Er+Ei)
-    double T1[NT][NT][2], T2[NT][NT][2], T3[NT][NT][2];
+        for (int b = 0; b < NT; ++b) {
+          T1[p][a][b][0] = T1[p][a][b][1] = 0.0; T2[p][a][b][0] = T2[p][a][b][1] = 0.0; T3[p][a][b][0] = T3[p][a][b][1] = 0.0;
+        }
+  }
+  // step 1: T_p^T[c'][a] += sum_c A_x[c,p,c'] * E[a][c]   (S1 = Ar Er, S2 = Ai Ei, S3 = (Ar+Ai)(Er+Ei));
+  // k-block outermost: 6*mx*ky independent accumulators between two MMAs on the same one.
 #pragma unroll
-    for (int a = 0; a < NT; ++a)
+  for (int kt = 0; kt < NT; ++kt) {
 #pragma unroll
-      for (int b = 0; b < NT; ++b) {
-        T1[a][b][0] = T1[a][b][1] = 0.0; T2[a][b][0] = T2[a][b][1] = 0.0; T3[a][b][0] = T3[a][b][1] = 0.0;
-      }
-    // fragments of the ket site tensor for this p: loaded up front (always in bounds of the padded block)
-    double2 xr[NT][NT], xi[NT][NT];
+    for (int e = 0; e < 2; ++e) {
+      if (2 * kt + e < kbx) {
 #pragma unroll
-    for (int mt = 0; mt < NT; ++mt)
-#pragma unroll
-      for (int kt = 0; kt < NT; ++kt) {
-        const int mtc = mt < MTx ? mt : MTx - 1, ktc = kt < KTx ? kt : KTx - 1;
-        const int fi = (((p * MTx + mtc) * KTx + ktc) * 2) * 32 + lane;
-        xr[mt][kt] = bx[fi];
-        xi[mt][kt] = bx[fi + 32];
-      }
-    // step 1: T^T[c'][a] += sum_c A_x[c,p,c'] * E[a][c]   (k-block outermost: 3*mx*ky independent accumulators)
-#pragma unroll
-    for (int kt = 0; kt < NT; ++kt) {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        if (2 * kt + e < kbx) {
+        for (int p = 0; p < 2; ++p) {
 #pragma unroll
           for (int mt = 0; mt < NT; ++mt) {
             if (mt < mx) {
-              const double ar = e ? xr[mt][kt].y : xr[mt][kt].x;
-              const double ai = e ? xi[mt][kt].y : xi[mt][kt].x;
+              const int mtc = mt < MTx ? mt : MTx - 1, ktc = kt < KTx ? kt : KTx - 1;
+              const int fi = (((p * MTx + mtc) * KTx + ktc) * 2) * 32 + lane;
+              const double2 fr = bx[fi], fm = bx[fi + 32];
+              const double ar = e ? fr.y : fr.x;
+              const double ai = e ? fm.y : fm.x;
               const double as = ar + ai;
 #pragma unroll
               for (int at = 0; at < NT; ++at) {
                 if (at < ky) {
-                  qk_dmma(T1[mt][at], ar, Er[at][kt][e]);
-                  qk_dmma(T2[mt][at], ai, Ei[at][kt][e]);
-                  qk_dmma(T3[mt][at], as, Es[at][kt][e]);
+                  if (STATIC && kt == 0 && e == 0) {
+                    qk_dmma_z(T1[p][mt][at], ar, Er[at][kt][e]);
+                    qk_dmma_z(T2[p][mt][at], ai, Ei[at][kt][e]);
+                    qk_dmma_z(T3[p][mt][at], as, Es[at][kt][e]);
+                  } else {
+                    qk_dmma(T1[p][mt][at], ar, Er[at][kt][e]);
+                    qk_dmma(T2[p][mt][at], ai, Ei[at][kt][e]);
+                    qk_dmma(T3[p][mt][at], as, Es[at][kt][e]);
+                  }
                 }
               }
             }
@@ -207,47 +211,59 @@ __device__ __forceinline__ void qk_site_step(double (&Er)[NT][NT][2], double (&E
         }
       }
     }
-    // bra fragments for step 2 (issued before the combine so the two overlap)
-    double2 yr[NT][NT], yi[NT][NT];
+  }
+  // T = (S1 - S2) + i (S3 - S1 - S2);  reuse T1 = Tr, T2 = Ti, T3 = Tr + Ti
 #pragma unroll
-    for (int bt = 0; bt < NT; ++bt)
-#pragma unroll
-      for (int at = 0; at < NT; ++at) {
-        const int btc = bt < MTy ? bt : MTy - 1, atc = at < KTy ? at : KTy - 1;
-        const int fi = (((p * MTy + btc) * KTy + atc) * 2) * 32 + lane;
-        yr[bt][at] = by[fi];
-        yi[bt][at] = by[fi + 32];
-      }
-    // T = (S1 - S2) + i (S3 - S1 - S2);  reuse T1 = Tr, T2 = Ti, T3 = Tr + Ti
+  for (int p = 0; p < 2; ++p)
 #pragma unroll
     for (int a = 0; a < NT; ++a)
 #pragma unroll
       for (int b = 0; b < NT; ++b)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const double u1 = T1[a][b][e], u2 = T2[a][b][e], u3 = T3[a][b][e];
-          T1[a][b][e] = u1 - u2;
-          T2[a][b][e] = u3 - u1 - u2;
-          T3[a][b][e] = u3 - 2.0 * u2;
+          const double u1 = T1[p][a][b][e], u2 = T2[p][a][b][e], u3 = T3[p][a][b][e];
+          T1[p][a][b][e] = u1 - u2;
+          T2[p][a][b][e] = u3 - u1 - u2;
+          T3[p][a][b][e] = u3 - 2.0 * u2;
         }
-    // step 2: E'[b'][c'] += sum_a conj(A_y[a,p,b']) * T[a][c']:  S1 = Ar Tr, S2 = Ai Ti, S3 = (Ar-Ai)(Tr+Ti)
+  // step 2: E'[b'][c'] += sum_{a,p} conj(A_y[a,p,b']) * T_p[a][c']:  S1 = Ar Tr, S2 = Ai Ti, S3 = (Ar-Ai)(Tr+Ti)
+  double F1[NT][NT][2], F2[NT][NT][2], F3[NT][NT][2];
+  if (!STATIC) {
 #pragma unroll
-    for (int at = 0; at < NT; ++at) {
+    for (int a = 0; a < NT; ++a)
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        if (2 * at + e < kby) {
+      for (int b = 0; b < NT; ++b) {
+        F1[a][b][0] = F1[a][b][1] = 0.0; F2[a][b][0] = F2[a][b][1] = 0.0; F3[a][b][0] = F3[a][b][1] = 0.0;
+      }
+  }
+#pragma unroll
+  for (int at = 0; at < NT; ++at) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      if (2 * at + e < kby) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
 #pragma unroll
           for (int bt = 0; bt < NT; ++bt) {
             if (bt < my) {
-              const double ar = e ? yr[bt][at].y : yr[bt][at].x;
-              const double ai = e ? yi[bt][at].y : yi[bt][at].x;
+              const int btc = bt < MTy ? bt : MTy - 1, atc = at < KTy ? at : KTy - 1;
+              const int fi = (((p * MTy + btc) * KTy + atc) * 2) * 32 + lane;
+              const double2 fr = by[fi], fm = by[fi + 32];
+              const double ar = e ? fr.y : fr.x;
+              const double ai = e ? fm.y : fm.x;
               const double ad = ar - ai;
 #pragma unroll
               for (int ct = 0; ct < NT; ++ct) {
                 if (ct < mx) {
-                  qk_dmma(F1[bt][ct], ar, T1[ct][at][e]);
-                  qk_dmma(F2[bt][ct], ai, T2[ct][at][e]);
-                  qk_dmma(F3[bt][ct], ad, T3[ct][at][e]);
+                  if (STATIC && at == 0 && e == 0 && p == 0) {
+                    qk_dmma_z(F1[bt][ct], ar, T1[p][ct][at][e]);
+                    qk_dmma_z(F2[bt][ct], ai, T2[p][ct][at][e]);
+                    qk_dmma_z(F3[bt][ct], ad, T3[p][ct][at][e]);
+                  } else {
+                    qk_dmma(F1[bt][ct], ar, T1[p][ct][at][e]);
+                    qk_dmma(F2[bt][ct], ai, T2[p][ct][at][e]);
+                    qk_dmma(F3[bt][ct], ad, T3[p][ct][at][e]);
+                  }
                 }
               }
             }
@@ -351,6 +367,12 @@ __global__ void __launch_bounds__(QK_GRAM_WARPS * 32, 1) qk_gram_dmma_kernel(con
       Er[a][b][0] = Er[a][b][1] = 0.0; Ei[a][b][0] = Ei[a][b][1] = 0.0; Es[a][b][0] = Es[a][b][1] = 0.0;
     }
   if (lane == 0) { Er[0][0][0] = 1.0; Es[0][0][0] = 1.0; }   // E_0 = [1]
+
+  // Two warps share each scheduler's DMMA pipe.  Started together they stay in lockstep (equal work,
+  // alternating MMAs) and reach their non-MMA sections (combines, loads, barrier) at the same time, when
+  // the pipe idles.  Starting the second warp of every scheduler about half a site late lets each
+  // warp's non-MMA section hide under the other's MMAs; the 3-stage pipeline absorbs the skew.
+  if (warp >= QK_GRAM_WARPS / 2 && P.skew_ns > 0) __nanosleep((unsigned)P.skew_ns);
 
   for (int s = 0; s < n; ++s) {
     const int st = s % QK_NS;
@@ -492,6 +514,26 @@ __global__ void __launch_bounds__(256) qk_dmma_peak_kernel(int iters, double* si
   if (s == 123.456) sink[0] = s;
 }
 
+// Variant with distinct A / B operand registers for every MMA (what a real contraction issues); the
+// kernel above feeds all eight MMAs of an iteration from the same two registers.
+__global__ void __launch_bounds__(256) qk_dmma_peak_kernel_distinct(int iters, double* sink) {
+  double acc[8][2], a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc[i][0] = 0.0; acc[i][1] = 0.0;
+    a[i] = 1.0 + 1e-9 * (threadIdx.x + 3 * i);
+    b[i] = 1.0 - 1e-9 * (threadIdx.x + 5 * i);
+  }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qk_dmma(acc[i], a[i], b[(i + it) & 7]);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += acc[i][0] + acc[i][1];
+  if (s == 123.456) sink[0] = s;
+}
+
 cudaError_t qk_run_dmma_peak(int iters, double* tflops) {
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
@@ -507,11 +549,13 @@ cudaError_t qk_run_dmma_peak(int iters, double* tflops) {
   }
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const bool distinct = getenv("QK_PEAK_DISTINCT") != nullptr;
   qk_dmma_peak_kernel<<<grid, block>>>(iters / 8 + 1, sink);   // warm-up
   float best = 1e30f;
   for (int rep = 0; rep < 3; ++rep) {
     cudaEventRecord(e0);
-    qk_dmma_peak_kernel<<<grid, block>>>(iters, sink);
+    if (distinct) qk_dmma_peak_kernel_distinct<<<grid, block>>>(iters, sink);
+    else qk_dmma_peak_kernel<<<grid, block>>>(iters, sink);
     cudaEventRecord(e1);
     e = cudaEventSynchronize(e1);
     if (e != cudaSuccess) break;

@@ -41,6 +41,7 @@ struct GramParams {
   double* K;
   int64_t ldk;
   int slot_x, slot_y;       // bytes reserved per state per pipeline stage
+  int skew_ns;              // start-up delay of the second warp of every scheduler (see qk_gram.cu)
 };
 // DMMA + bulk-copy pipeline kernel; requires max(D) <= 16.
 cudaError_t qk_launch_gram_dmma(const GramParams& P, int maxD, cudaStream_t stream);

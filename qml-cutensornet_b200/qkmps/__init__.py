@@ -14,7 +14,7 @@ import subprocess
 import numpy as np
 
 _HERE = pathlib.Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libqkmps.so"
+LIB_PATH = pathlib.Path(os.environ.get("QKMPS_LIB", _HERE / "libqkmps.so"))   # QKMPS_LIB: tuning builds only
 CSRC = _HERE.parent / "csrc"
 
 QK_TRUNC_ITENSORS = 0

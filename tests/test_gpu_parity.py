@@ -220,3 +220,26 @@ def test_errors(qk, cuda_device):
         build_kernel_matrix(SingleComm(), ans, X)
     with pytest.raises(RuntimeError):
         ans.circuit_for_data([0.1, 0.2])
+
+
+@pytest.mark.parametrize("backend", ["GPU", "CPU"])
+def test_main_driver_end_to_end(qk, cuda_device, backend, tmp_path, monkeypatch):
+    """the reference's command line on a synthetic Elliptic-shaped CSV, incl. the SVC sweep
+    and the reference's output files; the kernel matrices are checked against the exact statevector."""
+    import importlib
+    import sys
+    monkeypatch.chdir(tmp_path)
+    mk = importlib.import_module("make_synthetic_dataset")
+    (tmp_path / "datasets").mkdir()
+    mk.make(200, 600, seed=1).to_csv(tmp_path / "datasets" / "elliptic_synth.csv", index=False)
+    drv = importlib.import_module("main")
+    out = drv.main(["main.py", backend, "10", "2", "0.5", "1", "20", "20", "3", "elliptic_synth.csv"])
+    tag = "Nf10_r2_g0.5_p0.0_nn1_mslinear_Ntr20_s3_elliptic_synth"
+    for f in (f"kernels/train_{tag}.npy", f"kernels/test_{tag}.npy", f"data/train_{tag}.npy", f"data/test_{tag}.npy",
+              f"train_{tag}.json", f"test_{tag}.json"):
+        assert (tmp_path / f).exists(), f
+    assert out["k_train"].shape == (32, 32) and out["k_test"].shape == (8, 32)
+    assert np.load(tmp_path / f"data/test_{tag}.npy").shape == (11, 5)
+    emap = oracle.entanglement_graph(10, 1)
+    assert np.abs(out["k_train"] - oracle.statevector_gram(10, 2, 0.5, emap, out["x_train"])).max() < TOL
+    assert np.abs(out["k_test"] - oracle.statevector_gram(10, 2, 0.5, emap, out["x_train"], out["x_test"])).max() < TOL
