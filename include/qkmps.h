@@ -100,6 +100,11 @@ void qk_plan_destroy(qk_plan* plan);
 int qk_simulate(const qk_plan* plan, int device, const double* X_host, int N, int ldx, qk_batch** out);
 int qk_simulate_dev(const qk_plan* plan, int device, void* stream, const double* X_dev, int N, int ldx,
                     qk_batch** out);
+/* One datapoint with a memory trace: bytes_per_op[o] = sum of site-tensor bytes after op o of the compiled
+ * schedule (qk_plan_ops gives the ops).  Replaces the "MPS size (MiB)=" debug log of pytket-cutensornet that
+ * main_track_mem.py:168-172,254-256 captures and runs/mem_evol/plot.py:12-15 parses. */
+int qk_simulate_trace(const qk_plan* plan, int device, const double* x_host, int ldx, double* bytes_per_op,
+                      int max_ops, qk_batch** out);
 /* last stage-1 kernel time in ms (CUDA events on the launching stream) */
 int qk_batch_sim_ms(const qk_batch* batch, float* ms);
 

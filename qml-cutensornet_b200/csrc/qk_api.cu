@@ -189,6 +189,8 @@ static int batch_alloc(qk_batch* b) {
   return QK_OK;
 }
 
+static thread_local double* g_trace_dev = nullptr;   // set only inside qk_simulate_trace
+
 int qk_simulate_dev(const qk_plan* plan, int device, void* stream_v, const double* X_dev, int N, int ldx,
                     qk_batch** out) {
   if (!plan || !out) return fail(QK_ERR_ARG, "NULL argument");
@@ -228,6 +230,7 @@ int qk_simulate_dev(const qk_plan* plan, int device, void* stream_v, const doubl
   P.mode = plan->trunc_mode; P.cutoff = plan->trunc_error; P.fidelity_target = 1.0 - plan->trunc_error;
   P.value_of_zero = 1e-16;   // pytket-cutensornet Config default
   P.tol = 1e-15; P.max_sweeps = 60; P.rmax = plan->rmax; P.wr = plan->rmax * plan->rmax;
+  P.trace = g_trace_dev;
 
   QK_TRY(cudaEventCreate(&e0), "cudaEventCreate");
   QK_TRY(cudaEventCreate(&e1), "cudaEventCreate");
@@ -254,6 +257,25 @@ int qk_simulate(const qk_plan* plan, int device, const double* X_host, int N, in
   if (e != cudaSuccess) { pool_free(X_dev); return cuda_fail(e, "cudaMemcpy(X)"); }
   int rc = qk_simulate_dev(plan, device, nullptr, X_dev, N, ldx, out);
   pool_free(X_dev);
+  return rc;
+}
+
+int qk_simulate_trace(const qk_plan* plan, int device, const double* x_host, int ldx, double* bytes_per_op,
+                      int max_ops, qk_batch** out) {
+  if (!plan || !x_host || !bytes_per_op || !out) return fail(QK_ERR_ARG, "NULL argument");
+  const int nops = (int)plan->ops.size();
+  if (max_ops < nops) return fail(QK_ERR_ARG, "trace buffer smaller than the number of ops");
+  QK_CUDA(cudaSetDevice(device), "cudaSetDevice");
+  double* tr = nullptr;
+  QK_CUDA(pool_alloc_t(&tr, std::max<size_t>(nops, 1) * sizeof(double)), "cudaMalloc(trace)");
+  g_trace_dev = tr;
+  int rc = qk_simulate(plan, device, x_host, 1, ldx, out);
+  g_trace_dev = nullptr;
+  if (rc == QK_OK) {
+    cudaError_t e = cudaMemcpy(bytes_per_op, tr, nops * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = cuda_fail(e, "copy trace");
+  }
+  pool_free(tr);
   return rc;
 }
 

@@ -358,6 +358,7 @@ QK_DEV void qk_jacobi(SimCtx& c, int R, int C) {
             if (rpt <= 1) qk_pair_step<1>(wp, wq, jp, jq, R, C, sl, tpp, valid, tol2, floor2, &c.sh->rotated);
             else if (rpt <= 2) qk_pair_step<2>(wp, wq, jp, jq, R, C, sl, tpp, valid, tol2, floor2, &c.sh->rotated);
             else if (rpt <= 4) qk_pair_step<4>(wp, wq, jp, jq, R, C, sl, tpp, valid, tol2, floor2, &c.sh->rotated);
+            else if (rpt <= 8 && G >= 256) qk_pair_step<8>(wp, wq, jp, jq, R, C, sl, tpp, valid, tol2, floor2, &c.sh->rotated);
             else qk_pair_step_generic(wp, wq, jp, jq, R, C, sl, tpp, valid, tol2, floor2, &c.sh->rotated);
           QK_PAR_END
 #else
@@ -790,6 +791,15 @@ QK_DEV void qk_sim_datapoint(SimCtx& c, int dp) {
     if (op.kind <= QK_OP_RX) qk_op_1q<G>(c, op);
     else if (op.kind <= QK_OP_SWAP) qk_op_2q<G>(c, op);
     else qk_op_move<G>(c, op);
+    if (P->trace) {   // memory trace (reference main_track_mem.py logs "MPS size (MiB)=" per gate)
+      QK_PAR_BEGIN(tid)
+        if (tid == 0) {
+          double bytes = 0.0;
+          for (int s = 0; s < n; ++s) bytes += 32.0 * c.chi[s] * c.chi[s + 1];
+          P->trace[(size_t)dp * P->n_ops + o] = bytes;
+        }
+      QK_PAR_END
+    }
   }
   QK_PAR_BEGIN(tid)
     for (int b = tid; b <= n; b += G) P->chi[(size_t)dp * (n + 1) + b] = c.chi[b];

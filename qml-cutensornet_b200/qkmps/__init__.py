@@ -55,7 +55,7 @@ class QkOpView(ctypes.Structure):
 EXPORTS = [
     "qk_version", "qk_last_error", "qk_device_count",
     "qk_plan_create_gates", "qk_plan_create_ansatz", "qk_plan_info", "qk_plan_ops", "qk_plan_destroy",
-    "qk_simulate", "qk_simulate_dev", "qk_batch_sim_ms", "qk_batch_size", "qk_batch_info", "qk_batch_export",
+    "qk_simulate", "qk_simulate_dev", "qk_simulate_trace", "qk_batch_sim_ms", "qk_batch_size", "qk_batch_info", "qk_batch_export",
     "qk_batch_import", "qk_batch_max_chi", "qk_batch_destroy", "qk_frag_stride", "qk_batch_pack",
     "qk_gram_frags", "qk_gram_store", "qk_gram_host", "qk_dmma_peak",
 ]
@@ -251,6 +251,20 @@ def simulate_dev(plan: Plan, x_ptr: int, N: int, ldx: int, device: int = 0, stre
     _check(lib().qk_simulate_dev(plan._h, int(device), ctypes.c_void_p(stream), ctypes.c_void_p(x_ptr), int(N), int(ldx),
                                  ctypes.byref(h)))
     return Batch(h)
+
+
+def simulate_trace(plan: Plan, x, device: int = 0):
+    """Simulate one datapoint and return (Batch, [(op kind, site, MPS size in MiB after the op)]).
+
+    With ``log=True``-style use (see ``main_track_mem.py``) print ``f"MPS size (MiB)={mib}"`` per 2-qubit op.
+    """
+    x = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(1, -1))
+    ops = plan.ops()
+    tr = np.zeros(max(len(ops), 1))
+    h = ctypes.c_void_p()
+    _check(lib().qk_simulate_trace(plan._h, int(device), _p(x, ctypes.c_double), int(x.shape[1]), _p(tr, ctypes.c_double),
+                                   int(len(tr)), ctypes.byref(h)))
+    return Batch(h), [(o[0], o[1], float(b) / 2 ** 20) for o, b in zip(ops, tr)]
 
 
 def import_batch(states, device: int = 0) -> Batch:

@@ -34,8 +34,8 @@ def run(name, n, r, g, d, nx, ny, sample=6):
           f"offdiag range [{np.min(K):.2e}, {np.max(K - np.eye(*K.shape) if Y is None else K):.2e}]", flush=True)
     assert err < 1e-8
 
-#run("C5", 100, 2, 1.0, 2, 1000, 1000)
-#run("C5 g0.1", 100, 2, 0.1, 2, 1000, 1000)
+run("C5", 100, 2, 1.0, 2, 1000, 1000)
+run("C5 g0.1", 100, 2, 0.1, 2, 1000, 1000)
 run("C4 g0.1", 165, 4, 0.1, 4, 256, 0, sample=3)
 run("C2", 20, 2, 0.5, 1, 200, 0)
 run("runtime_scaling shape", 165, 2, 0.1, 1, 1280, 0, sample=4)

@@ -243,3 +243,18 @@ def test_main_driver_end_to_end(qk, cuda_device, backend, tmp_path, monkeypatch)
     emap = oracle.entanglement_graph(10, 1)
     assert np.abs(out["k_train"] - oracle.statevector_gram(10, 2, 0.5, emap, out["x_train"])).max() < TOL
     assert np.abs(out["k_test"] - oracle.statevector_gram(10, 2, 0.5, emap, out["x_train"], out["x_test"])).max() < TOL
+
+
+def test_memory_trace(qk, cuda_device):
+    """per-gate MPS size trace (main_track_mem.py equivalent)."""
+    import io
+    import importlib
+    mt = importlib.import_module("main_track_mem")
+    buf = io.StringIO()
+    sizes, batch = mt.track(12, 2, 1.0, 2, seed=0, out=buf)
+    lines = [l for l in buf.getvalue().splitlines() if l.startswith("MPS size (MiB)=")]
+    n2q = sum(1 for g in oracle.ansatz_gate_list(12, 2, 1.0, oracle.entanglement_graph(12, 2)) if len(g[1]) == 2)
+    assert len(lines) == n2q == len(sizes)
+    info = batch.info()
+    assert abs(sizes[-1] * 2 ** 20 - info["nbytes"][0]) < 1e-6        # final size = sum of tensor bytes (gpu:295)
+    assert sizes.max() >= sizes[-1] and sizes[0] > 0
