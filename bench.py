@@ -276,11 +276,15 @@ def run_ours(args):
     gates = ans.ansatz_circ.get_commands()
     plans = {}
 
-    def plan_factory(cap):
-        if cap not in plans:
-            plans[cap] = qkmps.Plan(n, gates, qkmps.QK_TRUNC_PYTKET, 1e-16, cap)
-        return plans[cap]
+    def plan_factory(cap, early_exit=False):
+        key = (cap, bool(early_exit))
+        if key not in plans:
+            plans[key] = qkmps.Plan(n, gates, qkmps.QK_TRUNC_PYTKET, 1e-16, cap,
+                                    qkmps.QK_PLAN_EARLY_EXIT if early_exit else 0)
+        return plans[key]
 
+    from gpu_backend.kernel_state_ansatz import _initial_cap
+    cap0 = args.chi if args.chi > 0 else _initial_cap(ans, 1e-16)
     X_dev = torch.from_numpy(X).to(f"cuda:{device}")
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=f"cuda:{device}")
     pairs = N * (N + 1) // 2
@@ -291,10 +295,10 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def step_device():
-        return build_gram(comm, plan_factory, n, X_dev, None, chi_cap=16, device=device, return_device=True)
+        return build_gram(comm, plan_factory, n, X_dev, None, chi_cap=cap0, device=device, return_device=True)
 
     def step_e2e():
-        return build_kernel_matrix(comm, ans, X, truncation_error=1e-16)
+        return build_kernel_matrix(comm, ans, X, truncation_error=1e-16, chi=cap0)
 
     for _ in range(max(args.warmup, 3)):
         step_device()
@@ -361,7 +365,7 @@ def run_ours(args):
         f2 = overlap_flops(chi_all)
     else:
         f2 = overlap_flops(chi_all) * (N / max(hi - lo, 1)) ** 2 / world   # estimate from rank 0's shard
-    b1 = sim_bytes(chi_all, plan_factory(prof["chi_cap"]).ops())
+    b1 = sim_bytes(chi_all, prof["plan_obj"].ops())
     stage2 = {"bound": "tensor", "achieved": f2 / (gram_mean * 1e-3) / 1e12, "peak": dmma_peak, "unit": "TFLOP/s",
               "frac": (f2 / (gram_mean * 1e-3) / 1e12 / dmma_peak) if dmma_peak else None, "traffic": None,
               "kernel": "qk_gram_dmma_kernel", "ms": gram_mean,
@@ -421,6 +425,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-budget", type=float, default=14.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chi", type=int, default=0, help="first bond cap tried (0: the backend's own choice)")
     ap.add_argument("--points", type=int, default=0, help="override the number of datapoints (experiments only)")
     args = ap.parse_args()
     if args.points > 0:

@@ -61,6 +61,10 @@ typedef enum {
                                      interactions; default: each run of them is applied as one sweep so the
                                      orthogonality centre never has to jump (same unitary, fewer gauge moves) */
 
+#define QK_PLAN_EARLY_EXIT 2      /* stop simulating a datapoint at its first bond-cap hit: its state is then
+                                     invalid and QK_FLAG_CAP_HIT (bit 0 of qk_batch_info flags) is set; lets a
+                                     caller try a small cap first and re-run only the states that need more */
+
 typedef struct qk_plan qk_plan;     /* compiled static op schedule of one ansatz (host object) */
 typedef struct qk_batch qk_batch;   /* device-resident batch of simulated MPS */
 
@@ -128,6 +132,10 @@ void qk_batch_destroy(qk_batch* batch);
  *      (multiples of 8, D[0] = D[n] = 8); it is plain device memory the caller may all-gather. ---- */
 int qk_frag_stride(int n_qubits, const int32_t* D, int64_t* bytes_per_state);
 int qk_batch_pack(const qk_batch* batch, const int32_t* D, void* frag_dev, void* stream);
+/* same, state i written at position dst_index[i] of the frag buffer (skipped if negative): merges the
+ * valid states of several batches (different bond caps) into one exchange buffer */
+int qk_batch_pack_scatter(const qk_batch* batch, const int32_t* D, void* frag_dev, const int32_t* dst_index,
+                          void* stream);
 
 /* ---- stage 2: replaces x_mps.vdot(y_mps) + |.|^2 (gpu_backend/kernel_state_ansatz.py:380-387) and
  *      abs(inner(y, x))^2 (KernelPkg/src/KernelPkg.jl:103-109).  K[y][x] = |<psi_y|psi_x>|^2 for the

@@ -22,8 +22,8 @@ _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if _PKG_ROOT not in sys.path:
     sys.path.insert(0, _PKG_ROOT)
 
-from qkmps import QK_TRUNC_ITENSORS, Plan  # noqa: E402
-from qkmps.ansatz import KernelStateAnsatzBase, structural_chi_bound  # noqa: E402
+from qkmps import QK_PLAN_EARLY_EXIT, QK_TRUNC_ITENSORS, Plan  # noqa: E402
+from qkmps.ansatz import KernelStateAnsatzBase, expected_chi, structural_chi_bound  # noqa: E402
 from qkmps.comm import Wtime  # noqa: E402
 from qkmps.engine import build_gram  # noqa: E402
 
@@ -64,13 +64,20 @@ def build_kernel_matrix(mpi_comm, ansatz, X, Y=None, info_file="info_file", trun
             raise RuntimeError(f"Unrecognised {name}.")
     plans = {}
 
-    def plan_factory(cap):
-        if cap not in plans:
-            plans[cap] = Plan(n_qubits, gates, QK_TRUNC_ITENSORS, float(truncation_error), cap)
-        return plans[cap]
+    def plan_factory(cap, early_exit=False):
+        key = (cap, bool(early_exit))
+        if key not in plans:
+            plans[key] = Plan(n_qubits, gates, QK_TRUNC_ITENSORS, float(truncation_error), cap,
+                              QK_PLAN_EARLY_EXIT if early_exit else 0)
+        return plans[key]
 
-    cap0 = int(chi) if chi is not None else int(
-        min(16, max(1, structural_chi_bound(ansatz.num_qubits, ansatz.reps, ansatz.entanglement_map))))
+    if chi is not None:
+        cap0 = int(chi)
+    else:
+        bound = max(1, structural_chi_bound(ansatz.num_qubits, ansatz.reps, ansatz.entanglement_map))
+        dist = max([abs(a - b) for a, b in ansatz.entanglement_map] or [0])
+        est = expected_chi(ansatz.gamma, bound, float(truncation_error), n_terms=ansatz.reps * dist)
+        cap0 = next((c for c in (4, 8, 16) if est <= c), 16)
     start_time = Wtime()
     K, prof = build_gram(mpi_comm, plan_factory, n_qubits, np.asarray(X), None if Y is None else np.asarray(Y),
                          chi_cap=cap0)

@@ -231,6 +231,7 @@ int qk_simulate_dev(const qk_plan* plan, int device, void* stream_v, const doubl
   P.value_of_zero = 1e-16;   // pytket-cutensornet Config default
   P.tol = 1e-15; P.max_sweeps = 60; P.rmax = plan->rmax; P.wr = plan->rmax * plan->rmax;
   P.trace = g_trace_dev;
+  P.early_exit = plan->early_exit;
 
   QK_TRY(cudaEventCreate(&e0), "cudaEventCreate");
   QK_TRY(cudaEventCreate(&e1), "cudaEventCreate");
@@ -408,33 +409,45 @@ int qk_frag_stride(int n_qubits, const int32_t* D, int64_t* bytes_per_state) {
   return QK_OK;
 }
 
-int qk_batch_pack(const qk_batch* b, const int32_t* D, void* frag_dev, void* stream_v) {
+int qk_batch_pack_scatter(const qk_batch* b, const int32_t* D, void* frag_dev, const int32_t* dst_index,
+                          void* stream_v) {
   if (!b || !frag_dev) return fail(QK_ERR_ARG, "NULL argument");
   int rc = check_D(b->n, D);
   if (rc != QK_OK) return rc;
   if (b->N == 0) return QK_OK;
   QK_CUDA(cudaSetDevice(b->device), "cudaSetDevice");
   cudaStream_t stream = (cudaStream_t)stream_v;
-  std::vector<int32_t> mc(b->n + 1);
-  rc = qk_batch_max_chi(b, mc.data());
-  if (rc != QK_OK) return rc;
-  for (int s = 0; s <= b->n; ++s)
-    if (mc[s] > D[s]) return fail(QK_ERR_ARG, "padded bond dimension smaller than a state's bond dimension");
+  // bond dimensions of the states that are actually packed must fit the padded dims
+  std::vector<int32_t> h((size_t)b->N * (b->n + 1));
+  QK_CUDA(cudaMemcpy(h.data(), b->chi, h.size() * sizeof(int32_t), cudaMemcpyDeviceToHost), "copy chi");
+  for (int i = 0; i < b->N; ++i) {
+    if (dst_index && dst_index[i] < 0) continue;
+    for (int s = 0; s <= b->n; ++s)
+      if (h[(size_t)i * (b->n + 1) + s] > D[s])
+        return fail(QK_ERR_ARG, "padded bond dimension smaller than a state's bond dimension");
+  }
   FragLayout L;
   std::vector<int64_t> off(b->n + 1);
   qk_frag_layout(b->n, D, &L, off.data());
-  int32_t* D_dev = nullptr; int64_t* off_dev = nullptr;
+  int32_t* D_dev = nullptr; int64_t* off_dev = nullptr; int32_t* dst_dev = nullptr;
   QK_CUDA(pool_alloc_t(&D_dev, (b->n + 1) * sizeof(int32_t)), "cudaMalloc(D)");
   cudaError_t e = pool_alloc_t(&off_dev, (b->n + 1) * sizeof(int64_t));
+  if (e == cudaSuccess && dst_index) e = pool_alloc_t(&dst_dev, (size_t)b->N * sizeof(int32_t));
   if (e == cudaSuccess) e = cudaMemcpyAsync(D_dev, D, (b->n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(off_dev, off.data(), (b->n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess && dst_index)
+    e = cudaMemcpyAsync(dst_dev, dst_index, (size_t)b->N * sizeof(int32_t), cudaMemcpyHostToDevice, stream);
   if (e == cudaSuccess)
     e = qk_launch_pack(b->n, b->N, b->store, b->state_stride, b->site_off_dev, b->chi, D_dev, off_dev, L.stride_bytes,
-                       L.data_bytes, frag_dev, stream);
+                       L.data_bytes, frag_dev, dst_dev, stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-  pool_free(D_dev); pool_free(off_dev);
+  pool_free(D_dev); pool_free(off_dev); pool_free(dst_dev);
   if (e != cudaSuccess) return cuda_fail(e, "pack kernel");
   return QK_OK;
+}
+
+int qk_batch_pack(const qk_batch* b, const int32_t* D, void* frag_dev, void* stream_v) {
+  return qk_batch_pack_scatter(b, D, frag_dev, nullptr, stream_v);
 }
 
 // ---------------------------------------------------------------- stage 2

@@ -59,14 +59,17 @@ __global__ void __launch_bounds__(256) qk_pack_kernel(int n, const c128* __restr
                                                       const int64_t* __restrict__ site_off,
                                                       const int32_t* __restrict__ chi, const int32_t* __restrict__ D,
                                                       const int64_t* __restrict__ frag_off, int64_t frag_stride,
-                                                      int64_t frag_data, unsigned char* __restrict__ frag) {
+                                                      int64_t frag_data, unsigned char* __restrict__ frag,
+                                                      const int32_t* __restrict__ dst_index) {
   const int s = blockIdx.x;
   const int i = blockIdx.y;
+  const int idst = dst_index ? dst_index[i] : i;   // position of state i in the frag buffer (< 0: skip)
+  if (idst < 0) return;
   const int Dl = D[s], Dr = D[s + 1];
   const int KT = Dl >> 3, MT = Dr >> 3;
   const int cl = chi[(size_t)i * (n + 1) + s], cr = chi[(size_t)i * (n + 1) + s + 1];
   const c128* A = store + (size_t)i * state_stride + site_off[s];
-  double* out = (double*)(frag + (size_t)i * frag_stride + frag_off[s]);
+  double* out = (double*)(frag + (size_t)idst * frag_stride + frag_off[s]);
   const int total = Dl * Dr * 4;
   for (int d = threadIdx.x; d < total; d += blockDim.x) {
     const int e = d & 1, lane = (d >> 1) & 31, h = (d >> 6) & 1;
@@ -85,18 +88,19 @@ __global__ void __launch_bounds__(256) qk_pack_kernel(int n, const c128* __restr
     out[d] = v;
   }
   if (s == 0) {
-    unsigned char* tc = frag + (size_t)i * frag_stride + frag_data;
+    unsigned char* tc = frag + (size_t)idst * frag_stride + frag_data;
     for (int b = threadIdx.x; b <= n; b += blockDim.x) tc[b] = (unsigned char)((chi[(size_t)i * (n + 1) + b] + 3) >> 2);
   }
 }
 
 cudaError_t qk_launch_pack(int n, int N, const c128* store, int64_t state_stride, const int64_t* site_off_dev,
                            const int32_t* chi_dev, const int32_t* D_dev, const int64_t* frag_off_dev,
-                           int64_t frag_stride_bytes, int64_t frag_data_bytes, void* frag_dev, cudaStream_t stream) {
+                           int64_t frag_stride_bytes, int64_t frag_data_bytes, void* frag_dev,
+                           const int32_t* dst_index_dev, cudaStream_t stream) {
   if (N <= 0) return cudaSuccess;
   dim3 grid(n, N);
   qk_pack_kernel<<<grid, 256, 0, stream>>>(n, store, state_stride, site_off_dev, chi_dev, D_dev, frag_off_dev,
-                                           frag_stride_bytes, frag_data_bytes, (unsigned char*)frag_dev);
+                                           frag_stride_bytes, frag_data_bytes, (unsigned char*)frag_dev, dst_index_dev);
   return cudaGetLastError();
 }
 

@@ -21,7 +21,8 @@ void qk_frag_layout(int n, const int32_t* D, FragLayout* L, int64_t* site_off_by
 
 cudaError_t qk_launch_pack(int n, int N, const c128* store, int64_t state_stride, const int64_t* site_off_dev,
                            const int32_t* chi_dev, const int32_t* D_dev, const int64_t* frag_off_dev,
-                           int64_t frag_stride_bytes, int64_t frag_data_bytes, void* frag_dev, cudaStream_t stream);
+                           int64_t frag_stride_bytes, int64_t frag_data_bytes, void* frag_dev, const int32_t* dst_index_dev,
+                           cudaStream_t stream);
 
 // ---- stage 2 ----
 struct GramParams {

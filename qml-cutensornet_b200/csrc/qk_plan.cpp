@@ -19,8 +19,7 @@ int qk_pick_threads(int chi_cap) {
     const int g = atoi(e);
     if (g == 32 || g == 64 || g == 128 || g == 256) return g;
   }
-  if (chi_cap <= 4) return 32;
-  if (chi_cap <= 8) return 64;
+  if (chi_cap <= 8) return 32;   // matrices <= 16x16: one warp, no block-level barriers to wait on (measured faster than 64)
   if (chi_cap <= 16) return 128;
   return 256;
 }
@@ -121,6 +120,7 @@ static void qk_reorder_commuting(std::vector<qk_gate>& g) {
 int qk_compile_plan(int n, const qk_gate* gates_in, int n_gates, int trunc_mode, double trunc_error, int chi_cap,
                     int flags, qk_plan* plan, std::string* err) {
   plan->reorder = (flags & QK_PLAN_LITERAL_ORDER) ? 0 : 1;
+  plan->early_exit = (flags & QK_PLAN_EARLY_EXIT) ? 1 : 0;
   if (n < 1) { *err = "n_qubits must be >= 1"; return QK_ERR_ARG; }
   if (n_gates < 0 || (n_gates > 0 && !gates_in)) { *err = "bad gate list"; return QK_ERR_ARG; }
   if (trunc_mode != QK_TRUNC_ITENSORS && trunc_mode != QK_TRUNC_PYTKET) { *err = "bad truncation mode"; return QK_ERR_ARG; }

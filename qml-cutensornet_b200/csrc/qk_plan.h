@@ -20,6 +20,7 @@ struct qk_plan {
   int64_t state_stride = 0;
   int n_2q = 0, n_1q = 0, n_moves = 0;
   int reorder = 1;                 // commutation-aware reordering of interaction runs (qk_plan.cpp)
+  int early_exit = 0;              // QK_PLAN_EARLY_EXIT
 };
 
 // Returns 0 or a negative qk_status; err receives a message.

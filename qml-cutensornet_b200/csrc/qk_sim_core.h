@@ -791,6 +791,7 @@ QK_DEV void qk_sim_datapoint(SimCtx& c, int dp) {
     if (op.kind <= QK_OP_RX) qk_op_1q<G>(c, op);
     else if (op.kind <= QK_OP_SWAP) qk_op_2q<G>(c, op);
     else qk_op_move<G>(c, op);
+    if (P->early_exit && op.kind >= QK_OP_XX && op.kind <= QK_OP_SWAP && (c.sh->flags & QK_FLAG_CAP_HIT)) break;
     if (P->trace) {   // memory trace (reference main_track_mem.py logs "MPS size (MiB)=" per gate)
       QK_PAR_BEGIN(tid)
         if (tid == 0) {

@@ -89,4 +89,5 @@ struct SimParams {
   int wr;                    // c128 elements per shared-memory matrix region = (2*capmax)^2
   int rmax;                  // 2*capmax
   double* trace;             // optional [N][n_ops]: MPS size in bytes after every op (memory trace), or NULL
+  int early_exit;            // stop a datapoint at its first bond-cap hit (state then invalid, flag set)
 };

@@ -22,8 +22,8 @@ _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if _PKG_ROOT not in sys.path:
     sys.path.insert(0, _PKG_ROOT)
 
-from qkmps import QK_TRUNC_PYTKET, Plan  # noqa: E402
-from qkmps.ansatz import KernelStateAnsatzBase, structural_chi_bound  # noqa: E402
+from qkmps import QK_PLAN_EARLY_EXIT, QK_TRUNC_PYTKET, Plan  # noqa: E402
+from qkmps.ansatz import KernelStateAnsatzBase, expected_chi, structural_chi_bound  # noqa: E402
 from qkmps.comm import Wtime  # noqa: E402
 from qkmps.engine import build_gram  # noqa: E402
 
@@ -35,8 +35,15 @@ class KernelStateAnsatz(KernelStateAnsatzBase):
         return self._bind(feature_values)
 
 
-def _initial_cap(ansatz) -> int:
-    return int(min(16, max(1, structural_chi_bound(ansatz.num_qubits, ansatz.reps, ansatz.entanglement_map))))
+def _initial_cap(ansatz, truncation_error) -> int:
+    """First bond cap: structural bound of the map, tightened by the angle-based estimate, on the cap ladder."""
+    bound = max(1, structural_chi_bound(ansatz.num_qubits, ansatz.reps, ansatz.entanglement_map))
+    dist = max([abs(a - b) for a, b in ansatz.entanglement_map] or [0])
+    est = expected_chi(ansatz.gamma, bound, float(truncation_error), n_terms=ansatz.reps * dist)
+    for cap in (4, 8, 16):
+        if est <= cap:
+            return cap
+    return 16
 
 
 def _percentiles(vals):
@@ -72,12 +79,14 @@ def build_kernel_matrix(mpi_comm, ansatz, X, Y=None, info_file=None, truncation_
     gates = ansatz.ansatz_circ.get_commands()
     plans = {}
 
-    def plan_factory(cap):
-        if cap not in plans:
-            plans[cap] = Plan(n_qubits, gates, QK_TRUNC_PYTKET, float(truncation_error), cap)
-        return plans[cap]
+    def plan_factory(cap, early_exit=False):
+        key = (cap, bool(early_exit))
+        if key not in plans:
+            plans[key] = Plan(n_qubits, gates, QK_TRUNC_PYTKET, float(truncation_error), cap,
+                              QK_PLAN_EARLY_EXIT if early_exit else 0)
+        return plans[key]
 
-    cap0 = int(chi) if chi is not None else _initial_cap(ansatz)
+    cap0 = int(chi) if chi is not None else _initial_cap(ansatz, truncation_error)
     plan_factory(cap0)
     if rank == root:
         duration = Wtime() - start_time

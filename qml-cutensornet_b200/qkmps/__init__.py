@@ -23,6 +23,7 @@ QK_FLAG_CAP_HIT = 1
 QK_FLAG_NO_CONVERGE = 2
 QK_ERR_LIMIT = -3
 QK_PLAN_LITERAL_ORDER = 1
+QK_PLAN_EARLY_EXIT = 2
 CHI_LIMIT = 32          # shared-memory-resident stage-1 kernel
 DMMA_D_LIMIT = 16       # register-resident tensor-core overlap kernel
 
@@ -57,6 +58,7 @@ EXPORTS = [
     "qk_plan_create_gates", "qk_plan_create_ansatz", "qk_plan_info", "qk_plan_ops", "qk_plan_destroy",
     "qk_simulate", "qk_simulate_dev", "qk_simulate_trace", "qk_batch_sim_ms", "qk_batch_size", "qk_batch_info", "qk_batch_export",
     "qk_batch_import", "qk_batch_max_chi", "qk_batch_destroy", "qk_frag_stride", "qk_batch_pack",
+    "qk_batch_pack_scatter",
     "qk_gram_frags", "qk_gram_store", "qk_gram_host", "qk_dmma_peak",
 ]
 
@@ -131,7 +133,9 @@ class Plan:
         self._h = ctypes.c_void_p()
         carr = gates_to_c(gates)
         if flags is None:
-            flags = QK_PLAN_LITERAL_ORDER if os.environ.get("QK_SCHEDULE", "") == "literal" else 0
+            flags = 0
+        if os.environ.get("QK_SCHEDULE", "") == "literal":
+            flags |= QK_PLAN_LITERAL_ORDER
         _check(lib().qk_plan_create_gates(int(n_qubits), carr, len(gates), int(trunc_mode),
                                           ctypes.c_double(trunc_error), int(chi_cap), int(flags),
                                           ctypes.byref(self._h)))
@@ -216,6 +220,14 @@ class Batch:
     def pack(self, D, frag_ptr: int, stream: int = 0):
         D = np.ascontiguousarray(D, dtype=np.int32)
         _check(lib().qk_batch_pack(self._h, _p(D, ctypes.c_int32), ctypes.c_void_p(frag_ptr), ctypes.c_void_p(stream)))
+
+    def pack_scatter(self, D, frag_ptr: int, dst_index, stream: int = 0):
+        """Pack state i at position ``dst_index[i]`` of the frag buffer (negative: skip)."""
+        D = np.ascontiguousarray(D, dtype=np.int32)
+        dst = np.ascontiguousarray(dst_index, dtype=np.int32)
+        assert dst.shape == (self.N,)
+        _check(lib().qk_batch_pack_scatter(self._h, _p(D, ctypes.c_int32), ctypes.c_void_p(frag_ptr),
+                                           _p(dst, ctypes.c_int32), ctypes.c_void_p(stream)))
 
     def gram_store(self, other=None) -> tuple[np.ndarray, float]:
         """CUDA-core cross-check kernel: K[y, x] with y over ``other`` (or self)."""

@@ -68,13 +68,68 @@ def _torch():
     return torch
 
 
-def _simulate_shard(plan_factory, X_shard, device, chi_cap, comm, n_qubits):
-    """Stage 1 on this rank's shard; doubles the bond cap (on every rank) while any state hit it.
+CAP_LADDER = (4, 8, 16, 24, 32)   # bond caps tried in turn; each has its own kernel configuration
 
-    ``X_shard`` is a host numpy array (copied through pinned memory) or a CUDA float64 tensor.
+
+class ShardStates:
+    """The simulated states of one rank's shard: one or more device batches (one per bond-cap level the
+    shard needed) plus, for every batch, which of its states are valid and where they sit in the shard."""
+
+    def __init__(self, n_local, n_qubits):
+        self.n_local, self.n_qubits = n_local, n_qubits
+        self.parts = []            # (Batch, info dict, valid local-in-batch indices, shard positions)
+        self.sim_ms = 0.0
+        self.launches = 0
+        self.cap = 1
+
+    def add(self, batch, info, ok_in_batch, shard_pos):
+        self.parts.append((batch, info, np.asarray(ok_in_batch, dtype=np.int64), np.asarray(shard_pos, dtype=np.int64)))
+
+    def info(self):
+        n, N = self.n_qubits, self.n_local
+        out = dict(chi=np.ones((N, n + 1), dtype=np.int32), fidelity=np.ones(N), trunc_weight=np.zeros(N),
+                   nbytes=np.zeros(N, dtype=np.int64), flags=np.zeros(N, dtype=np.int32), sweeps=np.zeros(N, dtype=np.int32))
+        for _, info, ok, pos in self.parts:
+            for k in out:
+                out[k][pos] = info[k][ok]
+        return out
+
+    def max_chi(self):
+        m = np.ones(self.n_qubits + 1, dtype=np.int32)
+        for _, info, ok, _ in self.parts:
+            if len(ok):
+                m = np.maximum(m, info["chi"][ok].max(axis=0))
+        return m
+
+    def pack(self, D, frag_ptr, stream):
+        for batch, _, ok, pos in self.parts:
+            if not len(ok):
+                continue
+            dst = np.full(batch.N, -1, dtype=np.int32)
+            dst[ok] = pos
+            batch.pack_scatter(D, frag_ptr, dst, stream)
+            self.launches += 1
+
+    def single_batch(self):
+        """The batch, if one batch holds every state of the shard in shard order (CUDA-core Gram fallback)."""
+        if len(self.parts) == 1:
+            b, _, ok, pos = self.parts[0]
+            if b.N == self.n_local and np.array_equal(ok, pos) and np.array_equal(ok, np.arange(self.n_local)):
+                return b
+        return None
+
+
+def _simulate_shard(plan_factory, X_shard, device, chi_cap, comm, n_qubits, escalate=True):
+    """Stage 1 on this rank's shard with per-datapoint bond-cap escalation.
+
+    ``chi_cap`` is the first cap tried (structural bound, clipped, or the user's ``chi``).  Bond dimensions
+    are data dependent (SURVEY.md hard part 1): the shard is simulated with ``QK_PLAN_EARLY_EXIT`` (a datapoint
+    stops at its first cap hit) and only the datapoints that hit the cap are re-run at the next cap of
+    ``CAP_LADDER``.  (Starting below the structural bound does not pay: at small bond dimension the kernel is
+    bound by the per-op latency of one datapoint, not by its shared-memory footprint -- measured, DESIGN.md.)
+    ``X_shard``: host numpy array (copied through pinned memory) or CUDA tensor.
     """
     torch = _torch()
-    from .comm import allreduce_max_int
     if isinstance(X_shard, torch.Tensor):
         xt = X_shard.contiguous()
     elif len(X_shard):
@@ -83,21 +138,40 @@ def _simulate_shard(plan_factory, X_shard, device, chi_cap, comm, n_qubits):
     else:
         xt = torch.empty((0, n_qubits), device=f"cuda:{device}", dtype=torch.float64)
     torch.cuda.current_stream().synchronize()
-    launches = 0
-    while True:
-        plan = plan_factory(chi_cap)
-        stream = torch.cuda.current_stream().cuda_stream
-        batch = simulate_dev(plan, xt.data_ptr(), int(xt.shape[0]), int(xt.shape[1]), device=device, stream=stream)
-        launches += 1 if xt.shape[0] else 0
+    n_local = int(xt.shape[0])
+    states = ShardStates(n_local, n_qubits)
+    ladder = [c for c in CAP_LADDER if c >= chi_cap]
+    if not ladder:
+        raise QkError(-3, f"bond dimension cap {chi_cap} above the shared-memory-resident limit (chi <= {CHI_LIMIT})")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def run(cap, idx, early):
+        plan = plan_factory(cap, early)
+        sub = xt if len(idx) == n_local and np.array_equal(idx, np.arange(n_local)) else xt[torch.from_numpy(idx).to(xt.device)]
+        batch = simulate_dev(plan, sub.data_ptr(), int(sub.shape[0]), int(sub.shape[1]), device=device, stream=stream)
         info = batch.info()
-        hit = int(np.any(info["flags"] & QK_FLAG_CAP_HIT)) if batch.N else 0
-        hit = allreduce_max_int(comm, hit)
-        if not hit:
-            return plan, batch, info, chi_cap, launches
-        if chi_cap >= CHI_LIMIT:
+        hit = (info["flags"] & QK_FLAG_CAP_HIT) != 0
+        ok = np.nonzero(~hit)[0]
+        states.add(batch, info, ok, idx[ok])
+        states.sim_ms += batch.sim_ms()
+        states.launches += 1
+        states.plan = plan
+        return idx[hit]
+
+    pending = np.arange(n_local, dtype=np.int64)
+    level = 0
+    while len(pending):
+        cap = ladder[level]
+        last = (level == len(ladder) - 1) or not escalate
+        states.cap = max(states.cap, cap)
+        pending = run(cap, pending, not last)
+        if last and len(pending):
             raise QkError(-3, f"bond dimension exceeds the shared-memory-resident limit (chi <= {CHI_LIMIT}); "
                               "the large-chi stage-1 path is not implemented")
-        chi_cap = min(max(chi_cap + 1, (chi_cap * 3 // 2 + 3) // 4 * 4), CHI_LIMIT)   # 4 -> 8 -> 12 -> 20 -> 32 ; 16 -> 24 -> 32
+        level += 1
+    if n_local == 0:
+        states.plan = plan_factory(ladder[0], False)
+    return states
 
 
 def build_gram(comm, plan_factory, n_qubits, X, Y=None, chi_cap=16, device=None, return_device=False):
@@ -124,60 +198,63 @@ def build_gram(comm, plan_factory, n_qubits, X, Y=None, chi_cap=16, device=None,
 
     # ---- stage 1 on this rank's shard(s)
     lo, hi = shard_bounds(Nx, size, rank)
-    plan, bx, info_x, chi_cap, nl = _simulate_shard(plan_factory, X[lo:hi], device, chi_cap, comm, n_qubits)
-    launches += nl
-    by, info_y = None, None
+    sx = _simulate_shard(plan_factory, X[lo:hi], device, chi_cap, comm, n_qubits)
+    info_x = sx.info()
+    sy, info_y = None, None
     if not symmetric:
         if not isinstance(Y, torch.Tensor):
             Y = np.asarray(Y, dtype=np.float64)
         ylo, yhi = shard_bounds(Ny, size, rank)
-        plan, by, info_y, chi_cap2, nl = _simulate_shard(plan_factory, Y[ylo:yhi], device, chi_cap, comm, n_qubits)
-        launches += nl
-        if chi_cap2 != chi_cap:   # Y needed a larger cap: redo X with it so both use one plan
-            chi_cap = chi_cap2
-            plan, bx, info_x, chi_cap, nl = _simulate_shard(plan_factory, X[lo:hi], device, chi_cap, comm, n_qubits)
-            launches += nl
-    prof["sim_ms_x"] = bx.sim_ms()
-    prof["sim_ms_y"] = by.sim_ms() if by is not None else 0.0
-    prof["chi_cap"] = chi_cap
+        sy = _simulate_shard(plan_factory, Y[ylo:yhi], device, chi_cap, comm, n_qubits)
+        info_y = sy.info()
+    prof["sim_ms_x"] = sx.sim_ms
+    prof["sim_ms_y"] = sy.sim_ms if sy is not None else 0.0
+    prof["chi_cap"] = max(sx.cap, sy.cap if sy is not None else 1)
     prof["info_x"], prof["info_y"] = info_x, info_y
-    prof["plan"] = plan.info()
+    prof["plan"] = sx.plan.info()
+    prof["plan_obj"] = sx.plan
     prof["shard"] = (lo, hi)
 
     # ---- exchange: batch-uniform padded dims, pack, all-gather
     t0 = time.perf_counter()
-    Dx = pad_dims(allreduce_max_array(comm, bx.max_chi()))
-    Dy = Dx if symmetric else pad_dims(allreduce_max_array(comm, by.max_chi()))
+    Dx = pad_dims(allreduce_max_array(comm, sx.max_chi()))
+    Dy = Dx if symmetric else pad_dims(allreduce_max_array(comm, sy.max_chi()))
     if int(max(Dx.max(), Dy.max())) > DMMA_D_LIMIT:
         # bond dimensions above the register-resident tensor-core kernel (D <= 16): CUDA-core FP64 kernel on
         # the unpadded stores.  It needs both batches on one device, so it is single-rank only for now.
         if size > 1:
             raise QkError(-3, f"padded bond dimension {int(max(Dx.max(), Dy.max()))} above the tensor-core overlap "
                               f"kernel's limit ({DMMA_D_LIMIT}) is only supported on one rank")
+        bx, by = sx.single_batch(), (sy.single_batch() if sy is not None else None)
+        if bx is None or (sy is not None and by is None):
+            # the CUDA-core kernel reads one store per side: re-simulate the shard at the final cap
+            sx = _simulate_shard(plan_factory, X[lo:hi], device, sx.cap, comm, n_qubits, escalate=False)
+            bx = sx.single_batch()
+            if sy is not None:
+                sy = _simulate_shard(plan_factory, Y[ylo:yhi], device, sy.cap, comm, n_qubits, escalate=False)
+                by = sy.single_batch()
         Kh, ms = bx.gram_store(by)
         if symmetric:
             Kh = 0.5 * (Kh + Kh.T)     # <y|x> and <x|y> are computed independently: symmetrise the rounding
-        prof.update(gram_ms=ms, Dx=Dx, Dy=Dy, launches=launches + 1, exchange_s=time.perf_counter() - t0,
+        prof.update(gram_ms=ms, Dx=Dx, Dy=Dy, launches=sx.launches + (sy.launches if sy is not None else 0) + 1,
+                    exchange_s=time.perf_counter() - t0,
                     frag_bytes_per_state=(0, 0), gram_kernel="qk_gram_store_kernel", no_converge=0)
         out = torch.from_numpy(Kh).to(dev) if return_device else Kh
         prof["total_s"] = time.perf_counter() - t_all
         return out, prof
     stream = torch.cuda.current_stream().cuda_stream
 
-    def packed(batch, D, n_total):
-        nonlocal launches
+    def packed(shard, D, n_total):
         stride = frag_stride(n_qubits, D)
         per = -(-n_total // size)
         local = torch.empty(max(per, 1) * stride, dtype=torch.uint8, device=dev)
-        if batch.N:
-            batch.pack(D, local.data_ptr(), stream)
-            launches += 1
+        shard.pack(D, local.data_ptr(), stream)
         if size == 1:
             return local, stride
         return allgather_bytes(comm, local), stride
 
-    fx, stride_x = packed(bx, Dx, Nx)
-    fy, stride_y = (fx, stride_x) if symmetric else packed(by, Dy, Ny)
+    fx, stride_x = packed(sx, Dx, Nx)
+    fy, stride_y = (fx, stride_x) if symmetric else packed(sy, Dy, Ny)
     torch.cuda.synchronize()
     prof["exchange_s"] = time.perf_counter() - t0
     prof["frag_bytes_per_state"] = (stride_x, stride_y)
@@ -190,6 +267,7 @@ def build_gram(comm, plan_factory, n_qubits, X, Y=None, chi_cap=16, device=None,
         ms = gram_frags(device, n_qubits, Dx, fx.data_ptr(), Nx, None if symmetric else Dy,
                         None if symmetric else fy.data_ptr(), Ny, tiles, symmetric, K.data_ptr(), Nx, stream)
         launches += 1
+    launches += sx.launches + (sy.launches if sy is not None else 0)
     prof["gram_ms"] = ms
     prof["Dx"], prof["Dy"] = Dx, Dy
     prof["launches"] = launches
@@ -200,6 +278,6 @@ def build_gram(comm, plan_factory, n_qubits, X, Y=None, chi_cap=16, device=None,
         out = K if return_device else K.cpu().numpy()
     torch.cuda.synchronize()
     prof["total_s"] = time.perf_counter() - t_all
-    bad = int(np.any(info_x["flags"] & QK_FLAG_NO_CONVERGE)) if bx.N else 0
+    bad = int(np.any(info_x["flags"] & QK_FLAG_NO_CONVERGE)) if len(info_x["flags"]) else 0
     prof["no_converge"] = bad
     return out, prof

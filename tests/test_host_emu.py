@@ -117,3 +117,20 @@ def test_emu_against_golden(emu):
         else:
             K = gram_from_mps(mx)
         assert np.abs(K - z["K_oracle"]).max() < 1e-10, f.name
+
+
+def test_emu_early_exit(emu):
+    """QK_PLAN_EARLY_EXIT (flag 2): a datapoint stops at its first cap hit and is flagged; datapoints that fit
+    are unaffected (their states equal the run without the flag)."""
+    n, r, g, d = 10, 2, 1.0, 2
+    X = oracle.synthetic_features(6, n, 2)
+    gates = oracle.ansatz_gate_list(n, r, g, oracle.entanglement_graph(n, d))
+    s_full, chi_full, st_full, _ = emu_simulate(emu, n, gates, X, chi_cap=16)
+    s_ee, chi_ee, st_ee, _ = emu_simulate(emu, n, gates, X, chi_cap=8, flags=2)
+    hit = (st_ee[:, 2].astype(int) & 1) != 0
+    need = chi_full.max(axis=1) > 8
+    assert np.array_equal(hit, need) and hit.any() and (~hit).any()
+    for i in np.nonzero(~hit)[0]:
+        assert np.array_equal(chi_ee[i], chi_full[i])
+        a, b = TensorsMPS(s_ee[i]), TensorsMPS(s_full[i])
+        assert abs(abs(mps_inner(a, b)) ** 2 - 1) < 1e-12
