@@ -258,3 +258,56 @@ def test_memory_trace(qk, cuda_device):
     info = batch.info()
     assert abs(sizes[-1] * 2 ** 20 - info["nbytes"][0]) < 1e-6        # final size = sum of tensor bytes (gpu:295)
     assert sizes.max() >= sizes[-1] and sizes[0] > 0
+
+
+@pytest.mark.parametrize("n,nx,ny", [(1, 3, 2), (2, 5, 0), (3, 1, 0), (6, 1, 1), (7, 9, 4), (5, 33, 17)])
+def test_edge_shapes(qk, cuda_device, n, nx, ny):
+    """Ragged / tiny inputs: one qubit, one datapoint, sizes that do not divide the kernel's 4x2 pair tile."""
+    from gpu_backend.kernel_state_ansatz import KernelStateAnsatz, build_kernel_matrix
+    from qkmps.engine import SingleComm
+    r, g, d = 2, 0.8, min(2, max(n - 1, 0))
+    emap = oracle.entanglement_graph(n, d)
+    X = oracle.synthetic_features(max(nx, 2), n, 4)[:nx]
+    Y = oracle.synthetic_features(max(ny, 2), n, 5)[:ny] if ny else None
+    ans = KernelStateAnsatz(n, r, g, emap)
+    K = build_kernel_matrix(SingleComm(), ans, X, Y, truncation_error=1e-16)
+    Kref = oracle.statevector_gram(n, r, g, emap, X, Y)
+    assert K.shape == Kref.shape
+    assert np.abs(K - Kref).max() < TOL
+
+
+def test_deterministic_and_order_independent(qk, cuda_device):
+    """Same inputs -> bit-identical Gram; permuting the datapoints permutes K (no cross-talk between states)."""
+    from gpu_backend.kernel_state_ansatz import KernelStateAnsatz, build_kernel_matrix
+    from qkmps.engine import SingleComm
+    n, r, g, d, N = 14, 2, 0.6, 2, 21
+    X = oracle.synthetic_features(N, n, 8)
+    ans = KernelStateAnsatz(n, r, g, oracle.entanglement_graph(n, d))
+    K1 = build_kernel_matrix(SingleComm(), ans, X, truncation_error=1e-16)
+    K2 = build_kernel_matrix(SingleComm(), ans, X, truncation_error=1e-16)
+    assert np.array_equal(K1, K2)
+    perm = np.random.default_rng(0).permutation(N)
+    K3 = build_kernel_matrix(SingleComm(), ans, X[perm], truncation_error=1e-16)
+    assert np.abs(K3 - K1[np.ix_(perm, perm)]).max() < 1e-12
+
+
+def test_truncation_control_changes_chi(qk, cuda_device):
+    """A looser truncation_error keeps fewer singular values and lowers the fidelity (pytket rule), and the
+    Gram error grows accordingly -- the truncation control is live, not decorative."""
+    n, r, g, d = 12, 2, 1.0, 2
+    ans = _ansatz(n, r, g, d)
+    X = oracle.synthetic_features(6, n, 3)
+    Ksv = oracle.statevector_gram(n, r, g, oracle.entanglement_graph(n, d), X)
+    prev_chi, prev_err = None, None
+    for err in (1e-16, 1e-8, 1e-3):
+        b = qk.simulate(_plan(qk, ans, 1, 16, err=err), X)
+        info = b.info()
+        ref = simulate_batch(n, r, g, oracle.entanglement_graph(n, d), X, cutoff=err, mode="pytket")
+        K, _ = b.gram_store()
+        e = np.abs(K - Ksv).max()
+        chi = info["chi"].max()
+        assert abs(info["fidelity"].mean() - np.mean([m.fidelity for m in ref])) < max(10 * err, 1e-12)
+        if prev_chi is not None:
+            assert chi <= prev_chi and e >= prev_err * 0.5
+        prev_chi, prev_err = chi, e
+    assert prev_chi < 16 and prev_err > 1e-6
