@@ -232,6 +232,7 @@ int qk_simulate_dev(const qk_plan* plan, int device, void* stream_v, const doubl
   P.tol = 1e-15; P.max_sweeps = 60; P.rmax = plan->rmax; P.wr = plan->rmax * plan->rmax;
   P.trace = g_trace_dev;
   P.early_exit = plan->early_exit;
+  P.floor_rel = 1e-28;
 
   QK_TRY(cudaEventCreate(&e0), "cudaEventCreate");
   QK_TRY(cudaEventCreate(&e1), "cudaEventCreate");

@@ -339,7 +339,7 @@ QK_DEV void qk_jacobi(SimCtx& c, int R, int C) {
   double total = 0.0;
   for (int t = 0; t < G; ++t) total += c.scr[t];
   QK_BARRIER();
-  const double floor2 = 1e-28 * total;
+  const double floor2 = c.P->floor_rel * total;
   if (C >= 2) {
     for (; sweep < c.P->max_sweeps; ++sweep) {
       for (int r = 0; r < nrounds; ++r) {
