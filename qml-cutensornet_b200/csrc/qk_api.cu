@@ -471,15 +471,33 @@ int qk_gram_frags(int device, void* stream_v, int n_qubits, const int32_t* Dx, c
 
   int TI = 0, TJ = 0;
   qk_gram_dmma_tile_shape(&TI, &TJ);
+  // L2 blocking: CTAs are scheduled in list order, so the pair tiles are emitted supertile by supertile,
+  // a supertile being S x S states whose packed bras + kets fit in about half of the 126 MB L2; every state
+  // is then fetched from HBM once per supertile instead of once per 8-pair tile.
+  int S = 8;
+  {
+    FragLayout Ltmp;
+    qk_frag_layout(n_qubits, Dx, &Ltmp, nullptr);
+    int64_t per_state = Ltmp.stride_bytes;
+    qk_frag_layout(n_qubits, Dy, &Ltmp, nullptr);
+    per_state = std::max<int64_t>(per_state, Ltmp.stride_bytes);
+    S = (int)std::max<int64_t>(8, ((int64_t)32 << 20) / std::max<int64_t>(per_state, 1));
+    S = std::max(8, S / 8 * 8);
+  }
   std::vector<int4> cta;
   for (int t = 0; t < n_tiles; ++t) {
     const int r0 = tiles[4 * t], r1 = tiles[4 * t + 1], c0 = tiles[4 * t + 2], c1 = tiles[4 * t + 3];
     if (r0 < 0 || c0 < 0 || r1 > Ny || c1 > Nx || r0 > r1 || c0 > c1) return fail(QK_ERR_ARG, "tile out of range");
-    for (int y0 = r0; y0 < r1; y0 += TJ)
-      for (int x0 = c0; x0 < c1; x0 += TI) {
-        const int ye = std::min(y0 + TJ, r1), xe = std::min(x0 + TI, c1);
-        if (symmetric && x0 > ye - 1) continue;   // whole sub-tile above the diagonal
-        cta.push_back(make_int4(y0, x0, ye, xe));
+    for (int sy = r0; sy < r1; sy += S)
+      for (int sx = c0; sx < c1; sx += S) {
+        const int sye = std::min(sy + S, r1), sxe = std::min(sx + S, c1);
+        if (symmetric && sx > sye - 1) continue;
+        for (int y0 = sy; y0 < sye; y0 += TJ)
+          for (int x0 = sx; x0 < sxe; x0 += TI) {
+            const int ye = std::min(y0 + TJ, sye), xe = std::min(x0 + TI, sxe);
+            if (symmetric && x0 > ye - 1) continue;   // whole sub-tile above the diagonal
+            cta.push_back(make_int4(y0, x0, ye, xe));
+          }
       }
   }
   if (cta.empty()) { if (ms_out) *ms_out = 0.f; return QK_OK; }
