@@ -65,6 +65,9 @@ typedef enum {
                                      invalid and QK_FLAG_CAP_HIT (bit 0 of qk_batch_info flags) is set; lets a
                                      caller try a small cap first and re-run only the states that need more */
 
+#define QK_PLAN_NO_FUSION 4       /* keep one SVD per 2-qubit gate (default: gates that follow each other on the
+                                     same bond are multiplied into one SVD and SWAP pairs cancel) */
+
 typedef struct qk_plan qk_plan;     /* compiled static op schedule of one ansatz (host object) */
 typedef struct qk_batch qk_batch;   /* device-resident batch of simulated MPS */
 

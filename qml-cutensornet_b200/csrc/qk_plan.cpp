@@ -121,6 +121,7 @@ int qk_compile_plan(int n, const qk_gate* gates_in, int n_gates, int trunc_mode,
                     int flags, qk_plan* plan, std::string* err) {
   plan->reorder = (flags & QK_PLAN_LITERAL_ORDER) ? 0 : 1;
   plan->early_exit = (flags & QK_PLAN_EARLY_EXIT) ? 1 : 0;
+  plan->fuse = (flags & QK_PLAN_NO_FUSION) ? 0 : 1;
   if (n < 1) { *err = "n_qubits must be >= 1"; return QK_ERR_ARG; }
   if (n_gates < 0 || (n_gates > 0 && !gates_in)) { *err = "bad gate list"; return QK_ERR_ARG; }
   if (trunc_mode != QK_TRUNC_ITENSORS && trunc_mode != QK_TRUNC_PYTKET) { *err = "bad truncation mode"; return QK_ERR_ARG; }
@@ -144,32 +145,56 @@ int qk_compile_plan(int n, const qk_gate* gates_in, int n_gates, int trunc_mode,
   if (plan->reorder) qk_reorder_commuting(gate_vec);
   const qk_gate* gates = gate_vec.data();
 
-  // validate + find, for every 2-qubit gate, the bond of the next one
-  std::vector<int> next2q(n_gates, -1);
-  int nxt = -1;
-  for (int i = n_gates - 1; i >= 0; --i) {
+  for (int i = 0; i < n_gates; ++i) {
     const qk_gate& g = gates[i];
     const bool two = (g.kind == QK_GATE_XX || g.kind == QK_GATE_ZZ || g.kind == QK_GATE_SWAP);
-    const bool one = (g.kind == QK_GATE_H || g.kind == QK_GATE_RZ || g.kind == QK_GATE_RX);
-    if (!one && !two) { *err = "Unrecognised gate."; return QK_ERR_ARG; }
-    if (g.q0 < 0 || g.q0 >= n) { *err = "gate qubit out of range"; return QK_ERR_ARG; }
-    if (two) {
-      if (g.q1 != g.q0 + 1 || g.q1 >= n) { *err = "two-qubit gates must act on adjacent sites (q, q+1)"; return QK_ERR_ARG; }
-    }
     if (g.kind != QK_GATE_H && g.kind != QK_GATE_SWAP && g.fa >= 0) {
       if (g.fa >= n || (two && (g.fb < 0 || g.fb >= n))) { *err = "feature index out of range"; return QK_ERR_ARG; }
     }
+  }
+
+  // Peephole fusion (not in literal mode): 2-qubit gates that follow each other on the same bond become one
+  // SVD (product of their 4x4 matrices); two SWAPs in a row cancel.  With the sweep order above this turns
+  // the per-interaction swap-in / swap-out routing of the reference into "walk the qubit out once, interact
+  // on the way, walk it back once": distance 2: 4 -> 3 SVDs per qubit, distance 4: 16 -> 7.
+  struct Item { bool two; int k; std::vector<qk_gate> g; };
+  std::vector<Item> items;
+  const size_t kMaxFuse = 4;
+  for (int i = 0; i < n_gates; ++i) {
+    const qk_gate& g = gates[i];
+    const bool two = (g.kind == QK_GATE_XX || g.kind == QK_GATE_ZZ || g.kind == QK_GATE_SWAP);
+    if (two && plan->reorder && plan->fuse && !items.empty() && items.back().two && items.back().k == g.q0 &&
+        items.back().g.size() < kMaxFuse) {
+      std::vector<qk_gate>& grp = items.back().g;
+      if (g.kind == QK_GATE_SWAP && grp.back().kind == QK_GATE_SWAP) {
+        grp.pop_back();
+        if (grp.empty()) items.pop_back();
+      } else {
+        grp.push_back(g);
+      }
+    } else {
+      Item it; it.two = two; it.k = g.q0; it.g.push_back(g);
+      items.push_back(it);
+    }
+  }
+  const int n_items = (int)items.size();
+  std::vector<int> next2q(n_items, -1);   // bond of the next 2-qubit group after item i
+  int nxt = -1;
+  for (int i = n_items - 1; i >= 0; --i) {
     next2q[i] = nxt;
-    if (two) nxt = g.q0;
+    if (items[i].two) nxt = items[i].k;
   }
 
   int centre = -1;   // -1: product state, every site is both left- and right-orthonormal
-  for (int i = 0; i < n_gates; ++i) {
-    const qk_gate& g = gates[i];
-    QkOp op; op.kind = g.kind; op.site = g.q0; op.fa = g.fa; op.fb = g.fb; op.dir = QK_DIR_RIGHT; op.pad = 0; op.coeff = g.coeff;
-    const bool two = (g.kind == QK_GATE_XX || g.kind == QK_GATE_ZZ || g.kind == QK_GATE_SWAP);
-    if (!two) { plan->ops.push_back(op); plan->n_1q++; continue; }
-    const int k = g.q0;
+  for (int i = 0; i < n_items; ++i) {
+    const Item& it = items[i];
+    if (!it.two) {
+      const qk_gate& g = it.g[0];
+      QkOp op; op.kind = g.kind; op.site = g.q0; op.fa = g.fa; op.fb = g.fb; op.dir = QK_DIR_RIGHT; op.pad = 0; op.coeff = g.coeff;
+      plan->ops.push_back(op); plan->n_1q++;
+      continue;
+    }
+    const int k = it.k;
     if (centre >= 0) {
       for (; centre < k; ++centre) {       // centre left of the pair: QR moves to the right
         QkOp mv; mv.kind = QK_OP_MOVE_R; mv.site = centre; mv.fa = mv.fb = -1; mv.dir = 0; mv.pad = 0; mv.coeff = 0.0;
@@ -181,9 +206,16 @@ int qk_compile_plan(int n, const qk_gate* gates_in, int n_gates, int trunc_mode,
       }
     }
     const int k2 = next2q[i];
-    op.dir = (k2 >= 0 && k2 + 1 <= k) ? QK_DIR_LEFT : QK_DIR_RIGHT;
-    centre = (op.dir == QK_DIR_LEFT) ? k : k + 1;
-    plan->ops.push_back(op); plan->n_2q++;
+    const int dir = (k2 >= 0 && k2 + 1 <= k) ? QK_DIR_LEFT : QK_DIR_RIGHT;
+    centre = (dir == QK_DIR_LEFT) ? k : k + 1;
+    const int ng = (int)it.g.size();
+    for (int j = 0; j < ng; ++j) {
+      const qk_gate& g = it.g[j];
+      QkOp op; op.kind = g.kind; op.site = k; op.fa = g.fa; op.fb = g.fb; op.dir = dir; op.coeff = g.coeff;
+      op.pad = (j + 1 < ng ? QK_OPF_CONT : 0) | (j > 0 ? QK_OPF_ACC : 0);
+      plan->ops.push_back(op);
+    }
+    plan->n_2q++;
   }
 
   // bond caps: user cap, clipped by the chain-edge bound 2^min(b, n-b)

@@ -21,6 +21,7 @@ struct qk_plan {
   int n_2q = 0, n_1q = 0, n_moves = 0;
   int reorder = 1;                 // commutation-aware reordering of interaction runs (qk_plan.cpp)
   int early_exit = 0;              // QK_PLAN_EARLY_EXIT
+  int fuse = 1;                    // fuse consecutive 2-qubit gates on one bond (off: QK_PLAN_NO_FUSION)
 };
 
 // Returns 0 or a negative qk_status; err receives a message.

@@ -63,6 +63,7 @@ struct SimCtx {
   double* nrm2;   // [rmax]
   int* order;     // [rmax]
   c128* gate;     // [16]
+  c128* gacc;     // [16] product of the gates of a fused group so far
   c128* diag;     // [rmax] diagonal of R (Householder)
   int* chi;       // [n+1] bond dimensions of the current datapoint
   double* x;      // [n] features of the current datapoint
@@ -76,7 +77,7 @@ QK_HD size_t qk_sim_smem_bytes(int n, int rmax, int G) {
   size_t b = 2 * wr * sizeof(c128);         // W, J
   b += (size_t)QK_SCR_PER_THREAD * G * sizeof(double);   // scr
   b += (size_t)rmax * sizeof(double);       // nrm2
-  b += 16 * sizeof(c128);                   // gate
+  b += 32 * sizeof(c128);                   // gate + fused-gate accumulator
   b += (size_t)rmax * sizeof(c128);         // diag
   b += (size_t)(n + 1) * sizeof(double);    // x (+pad)
   b += sizeof(SimShared);
@@ -93,7 +94,8 @@ QK_DEV void qk_sim_carve(SimCtx& c, const SimParams* P, unsigned char* smem, int
   c.scr = (double*)(c.J + wr);
   c.nrm2 = c.scr + QK_SCR_PER_THREAD * G;
   c.gate = (c128*)(c.nrm2 + P->rmax + (P->rmax & 1));
-  c.diag = c.gate + 16;
+  c.gacc = c.gate + 16;
+  c.diag = c.gacc + 16;
   c.x = (double*)(c.diag + P->rmax);
   c.sh = (SimShared*)(c.x + P->n + (P->n & 1));
   c.order = (int*)(c.sh + 1);
@@ -155,6 +157,21 @@ QK_DEV void qk_build_gate_2q(const QkOp& op, const double* x, c128* g) {
     for (int i = 0; i < 4; ++i) { g[i * 4 + i] = cmake(cs, 0); g[i * 4 + (3 - i)] = cmake(0, -sn); }
   } else {  // ZZ
     g[0] = cmake(cs, -sn); g[5] = cmake(cs, sn); g[10] = cmake(cs, sn); g[15] = cmake(cs, -sn);
+  }
+}
+
+// gate of this op, composed with the accumulated gate of its fused group (applied earlier => on the right)
+QK_DEV void qk_build_gate_2q_fused(const QkOp& op, const double* x, c128* g, const c128* gacc) {
+  qk_build_gate_2q(op, x, g);
+  if (op.pad & QK_OPF_ACC) {
+    c128 t[16];
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) {
+        c128 acc = cmake(0, 0);
+        for (int k = 0; k < 4; ++k) cfma(acc, g[i * 4 + k], gacc[k * 4 + j]);
+        t[i * 4 + j] = acc;
+      }
+    for (int i = 0; i < 16; ++i) g[i] = t[i];
   }
 }
 
@@ -481,6 +498,16 @@ QK_DEV void qk_truncate(SimCtx& c, int C, int capb) {
 // ------------------------------------------------------------------------------------------------
 template <int G>
 QK_DEV void qk_op_2q(SimCtx& c, const QkOp& op) {
+  if (op.pad & QK_OPF_CONT) {   // not the last gate of a fused group: only accumulate its matrix
+    QK_PAR_BEGIN(tid)
+      if (tid == 0) {
+        c128 g[16];
+        qk_build_gate_2q_fused(op, c.x, g, c.gacc);
+        for (int i = 0; i < 16; ++i) c.gacc[i] = g[i];
+      }
+    QK_PAR_END
+    return;
+  }
   const int k = op.site;
   const int ca = c.chi[k], cb = c.chi[k + 1], cc = c.chi[k + 2];
   const int m = 2 * ca, n2 = 2 * cc;
@@ -498,7 +525,7 @@ QK_DEV void qk_op_2q(SimCtx& c, const QkOp& op) {
   QK_PAR_BEGIN(tid)
     for (int i = tid; i < ca * 2 * cb; i += G) As[i] = A[i];
     for (int i = tid; i < cb * 2 * cc; i += G) Bs[i] = B[i];
-    if (tid == 0) qk_build_gate_2q(op, c.x, c.gate);
+    if (tid == 0) qk_build_gate_2q_fused(op, c.x, c.gate, c.gacc);
   QK_PAR_END
 
   // theta[(a,L),(R,c)] = sum_{l,r} g[(L,R),(l,r)] sum_b A[a,l,b] B[b,r,c]

@@ -44,12 +44,17 @@ enum {
 
 enum { QK_DIR_RIGHT = 0, QK_DIR_LEFT = 1 };
 
+// 2-qubit ops on the same bond that follow each other are fused into one SVD: every op but the last of
+// such a group only multiplies its 4x4 gate into an accumulator (QK_OPF_CONT), the others start from it
+// (QK_OPF_ACC).
+enum { QK_OPF_CONT = 1, QK_OPF_ACC = 2 };
+
 struct QkOp {
   int32_t kind;
   int32_t site;   // 1-qubit: the site; 2-qubit: left site k of (k, k+1); move: the site factorised
   int32_t fa, fb; // feature indices of the angle expression (fa < 0: constant angle)
   int32_t dir;    // 2-qubit ops: which factor receives the singular values
-  int32_t pad;
+  int32_t pad;    // QK_OPF_* flags
   double coeff;
 };
 

@@ -73,9 +73,9 @@ def test_plan_counts_and_schedule_invariants(qk, n, r, d, n2q):
     two_q = _replay(plan)
     ref = [(qk.GATE_KIND[nm], q[0]) for nm, q, _ in gates if len(q) == 2]
     assert [(k, s) for k, s, _, _ in two_q] == ref
-    # default: every run of (mutually commuting) XXPhase interactions applied as one sweep -> same
+    # reordering only: every run of (mutually commuting) XXPhase interactions applied as one sweep -> same
     # interactions, same routing per interaction, (almost) no gauge moves
-    plan2, _ = _plan(qk, n, r, 0.5, d)
+    plan2 = qk.Plan(n, gates, 0, 1e-16, 16, qk.QK_PLAN_NO_FUSION)
     info2 = plan2.info()
     assert (info2.n_ops_2q, info2.n_ops_1q) == (n2q, n * (r + 1))
     assert info2.n_moves <= r
@@ -83,9 +83,25 @@ def test_plan_counts_and_schedule_invariants(qk, n, r, d, n2q):
     assert sorted(two_q2) == sorted(two_q)
     xx = lambda ops: sorted((fa, fb) for k, s, fa, fb in ops if k == 3)   # noqa: E731
     assert xx(two_q2) == xx(two_q)
-    # 1-qubit layers still separate the repetitions: the k-th Rz layer sees the same interactions before it
+    # 1-qubit layers still separate the repetitions
     kinds = [k for k, *_ in plan2.ops()]
     assert kinds.count(1) == n * r and kinds.count(0) == n
+    # default = reordering + fusion: gates that follow each other on one bond share an SVD, SWAP pairs cancel;
+    # every interaction is still there exactly once, and fewer SVDs remain
+    plan3, _ = _plan(qk, n, r, 0.5, d)
+    info3 = plan3.info()
+    ops3 = plan3.ops()
+    assert xx([(k, s, fa, fb) for k, s, fa, fb, *_ in ops3]) == xx(two_q)
+    assert info3.n_moves <= r and info3.n_ops_1q == n * (r + 1)
+    n_swaps3 = sum(1 for k, *_ in ops3 if k == 5)
+    n_swaps = sum(1 for k, *_ in two_q if k == 5)
+    if d == 1:
+        assert info3.n_ops_2q == n2q and n_swaps3 == 0
+    else:
+        assert info3.n_ops_2q < n2q and n_swaps3 <= n_swaps
+        if d >= 3:
+            assert n_swaps3 < n_swaps            # walk out once / back once instead of per interaction
+    _replay(plan3)
 
 
 def test_plan_from_ansatz_equals_plan_from_gates(qk):
