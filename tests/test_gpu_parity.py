@@ -311,3 +311,27 @@ def test_truncation_control_changes_chi(qk, cuda_device):
             assert chi <= prev_chi and e >= prev_err * 0.5
         prev_chi, prev_err = chi, e
     assert prev_chi < 16 and prev_err > 1e-6
+
+
+def test_full_size_config3_properties(qk, cuda_device):
+    """BASELINE config 3 at its full size (1000 points, 50 qubits, 2 layers, distance 2; gamma 0.1 so that the
+    entries are not vanishingly small): size-independent properties of the Gram matrix, and agreement of the
+    tensor-core kernel with the CUDA-core kernel on a 64 x 1000 slab of rows."""
+    from gpu_backend.kernel_state_ansatz import build_kernel_matrix
+    from qkmps.engine import SingleComm
+    n, r, g, d, N = 50, 2, 0.1, 2, 1000
+    X = oracle.synthetic_features(N, n, 0)
+    ans = _ansatz(n, r, g, d)
+    K = build_kernel_matrix(SingleComm(), ans, X, truncation_error=1e-16)
+    assert K.shape == (N, N)
+    assert np.array_equal(K, K.T)
+    assert np.abs(np.diag(K) - 1).max() < 1e-10
+    assert K.min() >= 0 and K.max() <= 1 + 1e-10
+    assert np.linalg.eigvalsh(K).min() > -1e-9
+    bx = qk.simulate(_plan(qk, ans, 1, 8), X)
+    by = qk.simulate(_plan(qk, ans, 1, 8), X[100:164])
+    K0, _ = bx.gram_store(by)                       # K0[y, x], y over the slab
+    assert np.abs(K[100:164, :] - K0).max() < 1e-12
+    # rectangular call on the same data reproduces the slab (train x test path, C5 shape)
+    Kt = build_kernel_matrix(SingleComm(), ans, X, X[100:164], truncation_error=1e-16)
+    assert np.abs(Kt - K[100:164, :]).max() < 1e-12
