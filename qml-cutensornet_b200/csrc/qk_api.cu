@@ -465,7 +465,8 @@ int qk_gram_frags(int device, void* stream_v, int n_qubits, const int32_t* Dx, c
   if (ldk < Nx) return fail(QK_ERR_ARG, "ldk must be >= Nx");
   int maxD = 8;
   for (int s = 0; s <= n_qubits; ++s) maxD = std::max(maxD, std::max(Dx[s], Dy[s]));
-  if (maxD > 16) return fail(QK_ERR_LIMIT, "tensor-core overlap kernel supports padded bond dimensions <= 16");
+  if (maxD > 32) return fail(QK_ERR_LIMIT, "overlap kernels support padded bond dimensions <= 32");
+  const bool generic = maxD > 16;   // above the register-resident tensor-core kernel: CUDA-core kernel, same buffers
   QK_CUDA(cudaSetDevice(device), "cudaSetDevice");
   cudaStream_t stream = (cudaStream_t)stream_v;
 
@@ -522,8 +523,22 @@ int qk_gram_frags(int device, void* stream_v, int n_qubits, const int32_t* Dx, c
   memcpy(hbuf.data() + o_off, offx.data(), nb * sizeof(int64_t));
   memcpy(hbuf.data() + o_off + nb * sizeof(int64_t), offy.data(), nb * sizeof(int64_t));
   memcpy(hbuf.data() + t_off, cta.data(), bytes_t);
+  std::vector<int2> pair_list;
+  if (generic) {
+    for (const int4& t4 : cta)
+      for (int y = t4.x; y < t4.z; ++y)
+        for (int x = t4.y; x < t4.w; ++x)
+          if (!symmetric || x <= y) pair_list.push_back(make_int2(y, x));
+  }
+  int2* pairs_dev = nullptr;
   unsigned char* dbuf = nullptr;
   QK_CUDA(pool_alloc_t(&dbuf, hbuf.size()), "cudaMalloc(gram scratch)");
+  if (generic) {
+    cudaError_t ep = pool_alloc_t(&pairs_dev, std::max<size_t>(pair_list.size(), 1) * sizeof(int2));
+    if (ep == cudaSuccess)
+      ep = cudaMemcpyAsync(pairs_dev, pair_list.data(), pair_list.size() * sizeof(int2), cudaMemcpyHostToDevice, stream);
+    if (ep != cudaSuccess) { pool_free(dbuf); pool_free(pairs_dev); return cuda_fail(ep, "upload pair list"); }
+  }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   cudaError_t e = cudaMemcpyAsync(dbuf, hbuf.data(), hbuf.size(), cudaMemcpyHostToDevice, stream);
   GramParams P;
@@ -540,7 +555,9 @@ int qk_gram_frags(int device, void* stream_v, int n_qubits, const int32_t* Dx, c
   if (e == cudaSuccess) e = cudaEventCreate(&e0);
   if (e == cudaSuccess) e = cudaEventCreate(&e1);
   if (e == cudaSuccess) e = cudaEventRecord(e0, stream);
-  if (e == cudaSuccess) e = qk_launch_gram_dmma(P, maxD, stream);
+  if (e == cudaSuccess)
+    e = generic ? qk_launch_gram_frag_generic(P, pairs_dev, (int)pair_list.size(), maxD, stream)
+                : qk_launch_gram_dmma(P, maxD, stream);
   if (e == cudaSuccess) e = cudaEventRecord(e1, stream);
   if (e == cudaSuccess) e = cudaEventSynchronize(e1);
   float ms = 0.f;
@@ -548,6 +565,7 @@ int qk_gram_frags(int device, void* stream_v, int n_qubits, const int32_t* Dx, c
   if (e0) cudaEventDestroy(e0);
   if (e1) cudaEventDestroy(e1);
   pool_free(dbuf);
+  pool_free(pairs_dev);
   if (e != cudaSuccess) return cuda_fail(e, "stage-2 kernel");
   if (ms_out) *ms_out = ms;
   return QK_OK;

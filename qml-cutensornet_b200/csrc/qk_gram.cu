@@ -501,6 +501,73 @@ cudaError_t qk_launch_gram_store(int n, const c128* storeX, int64_t strideX, con
 }
 
 // ------------------------------------------------------------------------------------------------
+// Generic overlap kernel on the frag exchange format (CUDA cores, any padded D <= 32): one CTA per pair.
+// Used when a bond dimension exceeds the register-resident tensor-core kernel's D <= 16; because it reads
+// the same packed buffers, the multi-GPU exchange path is unchanged.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ c128 qk_frag_elem(const double* __restrict__ blk, int MT, int KT, int p, int c, int cp) {
+  const int kt = c >> 3, e = (c >> 2) & 1, mt = cp >> 3, r = cp & 7;
+  const int lane = (c & 3) | ((r >> 2) << 2) | ((r & 3) << 3);
+  const size_t base = ((((size_t)(p * MT + mt) * KT + kt) * 2) * 32 + lane) * 2 + e;   // h = 0 (real part)
+  return cmake(blk[base], blk[base + 64]);                                              // h = 1: +32 lanes * 2
+}
+
+__global__ void __launch_bounds__(64) qk_gram_frag_generic_kernel(const __grid_constant__ GramParams P,
+                                                                   const int2* __restrict__ pairs, int dmax) {
+  extern __shared__ __align__(16) unsigned char ssm[];
+  c128* E = (c128*)ssm;                         // [dmax][dmax]
+  c128* T = E + (size_t)dmax * dmax;            // [2*dmax][dmax]
+  const int y = pairs[blockIdx.x].x, x = pairs[blockIdx.x].y;
+  const unsigned char* bxs = P.fragX + (size_t)x * P.strideX;
+  const unsigned char* bys = P.fragY + (size_t)y * P.strideY;
+  const unsigned char* tcx = bxs + P.dataX;     // ceil(chi / 4) per bond
+  const unsigned char* tcy = bys + P.dataY;
+  // extents below are rounded up to 4, so E is read beyond the true bond dimension: it must be zero there
+  for (int i = threadIdx.x; i < dmax * dmax; i += blockDim.x) E[i] = cmake(i == 0 ? 1.0 : 0.0, 0.0);
+  __syncthreads();
+  for (int s = 0; s < P.n; ++s) {
+    const int KTx = P.Dx[s] >> 3, MTx = P.Dx[s + 1] >> 3, KTy = P.Dy[s] >> 3, MTy = P.Dy[s + 1] >> 3;
+    const int cxl = 4 * tcx[s], cxr = 4 * tcx[s + 1], cyl = 4 * tcy[s], cyr = 4 * tcy[s + 1];   // live extents
+    const double* ax = (const double*)(bxs + P.offx[s]);
+    const double* ay = (const double*)(bys + P.offy[s]);
+    // T[(a,p), c'] = sum_c E[a,c] A_x[c,p,c']        (E stored with row stride = live ket extent of bond s)
+    for (int idx = threadIdx.x; idx < cyl * 2 * cxr; idx += blockDim.x) {
+      const int a = idx / (2 * cxr);
+      const int rem = idx - a * 2 * cxr;
+      const int p = rem / cxr, cp = rem - p * cxr;
+      c128 acc = cmake(0, 0);
+      for (int c = 0; c < cxl; ++c) cfma(acc, E[a * cxl + c], qk_frag_elem(ax, MTx, KTx, p, c, cp));
+      T[idx] = acc;
+    }
+    __syncthreads();
+    // E'[b', c'] = sum_{a,p} conj(A_y[a,p,b']) T[(a,p), c']
+    for (int idx = threadIdx.x; idx < cyr * cxr; idx += blockDim.x) {
+      const int bp = idx / cxr, cp = idx - bp * cxr;
+      c128 acc = cmake(0, 0);
+      for (int a = 0; a < cyl; ++a)
+        for (int p = 0; p < 2; ++p) cfmac(acc, qk_frag_elem(ay, MTy, KTy, p, a, bp), T[(a * 2 + p) * cxr + cp]);
+      E[idx] = acc;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double v = E[0].x * E[0].x + E[0].y * E[0].y;
+    P.K[(size_t)y * P.ldk + x] = v;
+    if (P.symmetric) P.K[(size_t)x * P.ldk + y] = v;
+  }
+}
+
+cudaError_t qk_launch_gram_frag_generic(const GramParams& P, const int2* pairs_dev, int n_pairs, int maxD,
+                                        cudaStream_t stream) {
+  if (n_pairs <= 0) return cudaSuccess;
+  const size_t smem = (size_t)3 * maxD * maxD * sizeof(c128);
+  cudaError_t e = cudaFuncSetAttribute(qk_gram_frag_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  qk_gram_frag_generic_kernel<<<n_pairs, 64, smem, stream>>>(P, pairs_dev, maxD);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // DMMA peak microbenchmark (roofline denominator for stage 2; MEASURED_PEAKS.json has no FP64 figure)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) qk_dmma_peak_kernel(int iters, double* sink) {

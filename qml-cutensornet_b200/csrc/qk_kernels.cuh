@@ -47,6 +47,9 @@ struct GramParams {
 // DMMA + bulk-copy pipeline kernel; requires max(D) <= 16.
 cudaError_t qk_launch_gram_dmma(const GramParams& P, int maxD, cudaStream_t stream);
 void qk_gram_dmma_tile_shape(int* ti, int* tj);
+// CUDA-core kernel on the same frag buffers, any padded D <= 32 (one CTA per listed (y, x) pair)
+cudaError_t qk_launch_gram_frag_generic(const GramParams& P, const int2* pairs_dev, int n_pairs, int maxD,
+                                        cudaStream_t stream);
 
 // CUDA-core cross-check on the unpadded stores
 cudaError_t qk_launch_gram_store(int n, const c128* storeX, int64_t strideX, const int64_t* site_off_x,

@@ -219,29 +219,8 @@ def build_gram(comm, plan_factory, n_qubits, X, Y=None, chi_cap=16, device=None,
     t0 = time.perf_counter()
     Dx = pad_dims(allreduce_max_array(comm, sx.max_chi()))
     Dy = Dx if symmetric else pad_dims(allreduce_max_array(comm, sy.max_chi()))
-    if int(max(Dx.max(), Dy.max())) > DMMA_D_LIMIT:
-        # bond dimensions above the register-resident tensor-core kernel (D <= 16): CUDA-core FP64 kernel on
-        # the unpadded stores.  It needs both batches on one device, so it is single-rank only for now.
-        if size > 1:
-            raise QkError(-3, f"padded bond dimension {int(max(Dx.max(), Dy.max()))} above the tensor-core overlap "
-                              f"kernel's limit ({DMMA_D_LIMIT}) is only supported on one rank")
-        bx, by = sx.single_batch(), (sy.single_batch() if sy is not None else None)
-        if bx is None or (sy is not None and by is None):
-            # the CUDA-core kernel reads one store per side: re-simulate the shard at the final cap
-            sx = _simulate_shard(plan_factory, X[lo:hi], device, sx.cap, comm, n_qubits, escalate=False)
-            bx = sx.single_batch()
-            if sy is not None:
-                sy = _simulate_shard(plan_factory, Y[ylo:yhi], device, sy.cap, comm, n_qubits, escalate=False)
-                by = sy.single_batch()
-        Kh, ms = bx.gram_store(by)
-        if symmetric:
-            Kh = 0.5 * (Kh + Kh.T)     # <y|x> and <x|y> are computed independently: symmetrise the rounding
-        prof.update(gram_ms=ms, Dx=Dx, Dy=Dy, launches=sx.launches + (sy.launches if sy is not None else 0) + 1,
-                    exchange_s=time.perf_counter() - t0,
-                    frag_bytes_per_state=(0, 0), gram_kernel="qk_gram_store_kernel", no_converge=0)
-        out = torch.from_numpy(Kh).to(dev) if return_device else Kh
-        prof["total_s"] = time.perf_counter() - t_all
-        return out, prof
+    prof["gram_kernel"] = "qk_gram_dmma_kernel" if int(max(Dx.max(), Dy.max())) <= DMMA_D_LIMIT else \
+        "qk_gram_frag_generic_kernel"   # D > 16: CUDA-core kernel on the same packed buffers (any rank count)
     stream = torch.cuda.current_stream().cuda_stream
 
     def packed(shard, D, n_total):

@@ -20,7 +20,7 @@ def main():
     comm = init_from_env("nccl")
     rank, size = comm.Get_rank(), comm.Get_size()
     worst = 0.0
-    for (n, r, g, d, nx, ny) in [(10, 2, 0.5, 1, 40, 13), (12, 2, 0.7, 2, 37, 9), (14, 2, 0.1, 2, 21, 21)]:
+    for (n, r, g, d, nx, ny) in [(10, 2, 0.5, 1, 40, 13), (12, 2, 0.7, 2, 37, 9), (14, 2, 0.1, 2, 21, 21), (10, 3, 0.5, 4, 10, 6)]:
         emap = oracle.entanglement_graph(n, d)
         X = oracle.synthetic_features(nx, n, 0)
         Y = oracle.synthetic_features(ny, n, 1)
@@ -31,7 +31,10 @@ def main():
             e1 = np.abs(K - oracle.statevector_gram(n, r, g, emap, X)).max()
             e2 = np.abs(Kt - oracle.statevector_gram(n, r, g, emap, X, Y)).max()
             assert K.shape == (nx, nx) and Kt.shape == (ny, nx)
-            assert np.array_equal(K, K.T)
+            if not np.array_equal(K, K.T):
+                bad = np.argwhere(K != K.T)
+                print('ASYM', (n, r, g, d, nx, ny), len(bad), bad[:6].tolist(), np.abs(K - K.T).max(), flush=True)
+            assert np.abs(K - K.T).max() < 1e-14
             worst = max(worst, e1, e2)
         else:
             assert K is None and Kt is None

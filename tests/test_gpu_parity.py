@@ -335,3 +335,23 @@ def test_full_size_config3_properties(qk, cuda_device):
     # rectangular call on the same data reproduces the slab (train x test path, C5 shape)
     Kt = build_kernel_matrix(SingleComm(), ans, X, X[100:164], truncation_error=1e-16)
     assert np.abs(Kt - K[100:164, :]).max() < 1e-12
+
+
+def test_large_bond_dimension_path(qk, cuda_device):
+    """Bond dimensions above 16 (here up to ~32): cap escalation 16 -> 24 -> 32 in stage 1 and the generic
+    overlap kernel on the packed buffers in stage 2, through the reference-facing entry point (ITensors rule:
+    the pytket rule keeps rounding-noise values and would ask for more than the 32 the kernels hold)."""
+    from cpu_backend.kernel_state_ansatz import KernelStateAnsatz, build_kernel_matrix
+    from qkmps.engine import SingleComm
+    n, r, g, d = 10, 3, 0.5, 4      # 10 qubits: bond dimension structurally <= 32
+    emap = oracle.entanglement_graph(n, d)
+    X = oracle.synthetic_features(9, n, 0)
+    Y = oracle.synthetic_features(4, n, 1)
+    ans = KernelStateAnsatz(n, r, g, emap)
+    K = build_kernel_matrix(SingleComm(), ans, X, info_file="/tmp/qk_big", truncation_error=1e-16)
+    prof = build_kernel_matrix.last_profile
+    assert prof["info_x"]["chi"].max() > 16 and prof["gram_kernel"] == "qk_gram_frag_generic_kernel"
+    assert np.abs(K - oracle.statevector_gram(n, r, g, emap, X)).max() < TOL
+    assert np.array_equal(K, K.T)
+    Kt = build_kernel_matrix(SingleComm(), ans, X, Y, info_file="/tmp/qk_big", truncation_error=1e-16)
+    assert np.abs(Kt - oracle.statevector_gram(n, r, g, emap, X, Y)).max() < TOL
