@@ -233,6 +233,7 @@ int qk_simulate_dev(const qk_plan* plan, int device, void* stream_v, const doubl
   P.trace = g_trace_dev;
   P.early_exit = plan->early_exit;
   P.floor_rel = 1e-28;
+  P.abs_rel = 0.0;
 
   QK_TRY(cudaEventCreate(&e0), "cudaEventCreate");
   QK_TRY(cudaEventCreate(&e1), "cudaEventCreate");

@@ -217,12 +217,13 @@ QK_DEV double qk_rcp(double x) {
 // was below QK_QUAD_EPS = 1e-9 leaves every pair below ~1e-18 after its own rotations: the usual
 // "empty" verification sweep (a quarter of the work at ~3 sweeps per SVD) is not needed.
 #define QK_QUAD_EPS2 1e-18
-QK_DEV int qk_rotation(double a, double b, double gr, double gi, double tol2, double floor2, double& cs, c128& f) {
+QK_DEV int qk_rotation(double a, double b, double gr, double gi, double tol2, double floor2, double abs2, double& cs,
+                       c128& f) {
   const double g2 = gr * gr + gi * gi;
   // a column whose weight is < 1e-28 of the total is numerically zero (rank-deficient theta is the
   // common case); rotating it again only chases rounding noise
   const bool live = (a > floor2) && (b > floor2);
-  if (!(live && g2 > tol2 * a * b && g2 > 0.0)) return 0;
+  if (!(live && g2 > tol2 * a * b && g2 > abs2)) return 0;
   const double tau = b - a;
   const double rh = qk_rsqrt(fma(tau, tau, 4.0 * g2));
   const double x = fma(0.5 * fabs(tau), rh, 0.5);
@@ -256,7 +257,7 @@ QK_DEV void qk_rotate_rows(c128* up, c128* uq, int rows, int sl, int tpp, double
 template <int RPT>
 __device__ __forceinline__ void qk_pair_step(c128* __restrict__ wp, c128* __restrict__ wq, c128* __restrict__ jp,
                                              c128* __restrict__ jq, int R, int C, int sl, int tpp, bool valid,
-                                             double tol2, double floor2, int* rotated) {
+                                             double tol2, double floor2, double abs2, int* rotated) {
   c128 xp[RPT], xq[RPT];
   double a = 0, b = 0, gr = 0, gi = 0;
 #pragma unroll
@@ -276,7 +277,7 @@ __device__ __forceinline__ void qk_pair_step(c128* __restrict__ wp, c128* __rest
     gi += __shfl_xor_sync(0xffffffffu, gi, off);
   }
   double cs; c128 f;
-  const int rot = valid ? qk_rotation(a, b, gr, gi, tol2, floor2, cs, f) : 0;
+  const int rot = valid ? qk_rotation(a, b, gr, gi, tol2, floor2, abs2, cs, f) : 0;
   if (rot) {
 #pragma unroll
     for (int k = 0; k < RPT; ++k) {
@@ -303,7 +304,8 @@ __device__ __forceinline__ void qk_pair_step(c128* __restrict__ wp, c128* __rest
 
 // Same step for any number of rows per thread (rows are re-read for the rotation).
 __device__ __forceinline__ void qk_pair_step_generic(c128* wp, c128* wq, c128* jp, c128* jq, int R, int C, int sl,
-                                                     int tpp, bool valid, double tol2, double floor2, int* rotated) {
+                                                     int tpp, bool valid, double tol2, double floor2, double abs2,
+                                                     int* rotated) {
   double a = 0, b = 0, gr = 0, gi = 0;
   if (valid) {
     for (int row = sl; row < R; row += tpp) {
@@ -321,7 +323,7 @@ __device__ __forceinline__ void qk_pair_step_generic(c128* wp, c128* wq, c128* j
     gi += __shfl_xor_sync(0xffffffffu, gi, off);
   }
   double cs; c128 f;
-  const int rot = valid ? qk_rotation(a, b, gr, gi, tol2, floor2, cs, f) : 0;
+  const int rot = valid ? qk_rotation(a, b, gr, gi, tol2, floor2, abs2, cs, f) : 0;
   if (rot) {
     qk_rotate_rows(wp, wq, R, sl, tpp, cs, f);
     qk_rotate_rows(jp, jq, C, sl, tpp, cs, f);
@@ -357,6 +359,9 @@ QK_DEV void qk_jacobi(SimCtx& c, int R, int C) {
   for (int t = 0; t < G; ++t) total += c.scr[t];
   QK_BARRIER();
   const double floor2 = c.P->floor_rel * total;
+  // inner products below abs_rel * total are rounding-level relative to the dominant columns: rotating
+  // them only polishes directions whose weight is far below any truncation threshold
+  const double abs2 = c.P->abs_rel * c.P->abs_rel * total * total;
   if (C >= 2) {
     for (; sweep < c.P->max_sweeps; ++sweep) {
       for (int r = 0; r < nrounds; ++r) {
@@ -372,11 +377,11 @@ QK_DEV void qk_jacobi(SimCtx& c, int R, int C) {
             c128* wq = W + (size_t)q * ldw;
             c128* jp = J + (size_t)p * C;
             c128* jq = J + (size_t)q * C;
-            if (rpt <= 1) qk_pair_step<1>(wp, wq, jp, jq, R, C, sl, tpp, valid, tol2, floor2, &c.sh->rotated);
-            else if (rpt <= 2) qk_pair_step<2>(wp, wq, jp, jq, R, C, sl, tpp, valid, tol2, floor2, &c.sh->rotated);
-            else if (rpt <= 4) qk_pair_step<4>(wp, wq, jp, jq, R, C, sl, tpp, valid, tol2, floor2, &c.sh->rotated);
-            else if (rpt <= 8 && G >= 256) qk_pair_step<8>(wp, wq, jp, jq, R, C, sl, tpp, valid, tol2, floor2, &c.sh->rotated);
-            else qk_pair_step_generic(wp, wq, jp, jq, R, C, sl, tpp, valid, tol2, floor2, &c.sh->rotated);
+            if (rpt <= 1) qk_pair_step<1>(wp, wq, jp, jq, R, C, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
+            else if (rpt <= 2) qk_pair_step<2>(wp, wq, jp, jq, R, C, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
+            else if (rpt <= 4) qk_pair_step<4>(wp, wq, jp, jq, R, C, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
+            else if (rpt <= 8 && G >= 256) qk_pair_step<8>(wp, wq, jp, jq, R, C, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
+            else qk_pair_step_generic(wp, wq, jp, jq, R, C, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
           QK_PAR_END
 #else
           QK_PAR_BEGIN(tid)
@@ -410,7 +415,7 @@ QK_DEV void qk_jacobi(SimCtx& c, int R, int C) {
                 a += s4[0]; b += s4[1]; gr += s4[2]; gi += s4[3];
               }
               double cs; c128 f;
-              const int rot = qk_rotation(a, b, gr, gi, tol2, floor2, cs, f);
+              const int rot = qk_rotation(a, b, gr, gi, tol2, floor2, abs2, cs, f);
               if (rot) {
                 qk_rotate_rows(W + (size_t)p * ldw, W + (size_t)q * ldw, R, sl, tpp, cs, f);
                 qk_rotate_rows(J + (size_t)p * C, J + (size_t)q * C, C, sl, tpp, cs, f);

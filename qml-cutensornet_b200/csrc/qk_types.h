@@ -96,4 +96,5 @@ struct SimParams {
   double* trace;             // optional [N][n_ops]: MPS size in bytes after every op (memory trace), or NULL
   int early_exit;            // stop a datapoint at its first bond-cap hit (state then invalid, flag set)
   double floor_rel;          // Jacobi: columns below floor_rel * total weight are treated as numerically zero
+  double abs_rel;            // Jacobi: no rotation when |x^dag y| <= abs_rel * total weight
 };

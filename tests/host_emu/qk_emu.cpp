@@ -47,6 +47,7 @@ long long qk_emu_simulate(int n, const qk_gate* gates, int n_gates, int trunc_mo
   P.mode = trunc_mode; P.cutoff = trunc_error; P.fidelity_target = 1.0 - trunc_error; P.value_of_zero = 1e-16;
   P.tol = getenv("QK_EMU_TOL") ? atof(getenv("QK_EMU_TOL")) : 1e-15; P.max_sweeps = getenv("QK_EMU_SWEEPS") ? atoi(getenv("QK_EMU_SWEEPS")) : 60; P.rmax = plan.rmax; P.wr = plan.rmax * plan.rmax; P.trace = nullptr; P.early_exit = (flags & 2) ? 1 : 0;
   P.floor_rel = getenv("QK_EMU_FLOOR") ? atof(getenv("QK_EMU_FLOOR")) : 1e-28;
+  P.abs_rel = getenv("QK_EMU_ABS") ? atof(getenv("QK_EMU_ABS")) : 0.0;
   size_t bytes = qk_sim_smem_bytes(n, plan.rmax, G);
   unsigned char* smem = (unsigned char*)aligned_alloc(64, (bytes + 63) & ~(size_t)63);
   for (int dp = 0; dp < N; ++dp) {
