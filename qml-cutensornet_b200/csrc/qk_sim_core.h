@@ -469,7 +469,8 @@ QK_DEV void qk_truncate(SimCtx& c, int C, int capb) {
     }
   } else {
     int m = 0;
-    for (int t = 0; t < C; ++t) if (sqrt(c.nrm2[c.order[t]]) >= P->value_of_zero) ++m;
+    const double zero2 = P->value_of_zero * P->value_of_zero;
+    for (int t = 0; t < C; ++t) if (c.nrm2[c.order[t]] >= zero2) ++m;
     if (m < 1) m = 1;
     double denom = 0.0;
     for (int t = 0; t < m; ++t) denom += c.nrm2[c.order[t]];
@@ -584,6 +585,8 @@ QK_DEV void qk_op_2q(SimCtx& c, const QkOp& op) {
         rk += (u > v) || (u == v && i < j);
       }
       c.order[rk] = j;
+      const double sg = sqrt(v);                       // singular value and its inverse, once per column
+      c.diag[j] = cmake(sg, sg > 0.0 ? 1.0 / sg : 0.0);
     }
   QK_PAR_END
   QK_PAR_BEGIN(tid)
@@ -598,8 +601,7 @@ QK_DEV void qk_op_2q(SimCtx& c, const QkOp& op) {
     for (int idx = tid; idx < m * keep; idx += G) {
       const int row = idx / keep, t = idx - row * keep;
       const int j = c.order[t];
-      const double sg = sqrt(c.nrm2[j]);
-      const double isg = sg > 0.0 ? 1.0 / sg : 0.0;
+      const double sg = c.diag[j].x, isg = c.diag[j].y;
       c128 v;
       if (!transposed) v = cscale(W[row + (size_t)j * ldw], right ? isg : renorm);        // W = U S
       else v = cscale(J[row + (size_t)j * C], right ? 1.0 : sg * renorm);                // U = J
@@ -608,8 +610,7 @@ QK_DEV void qk_op_2q(SimCtx& c, const QkOp& op) {
     for (int idx = tid; idx < keep * n2; idx += G) {
       const int t = idx / n2, col = idx - t * n2;
       const int j = c.order[t];
-      const double sg = sqrt(c.nrm2[j]);
-      const double isg = sg > 0.0 ? 1.0 / sg : 0.0;
+      const double sg = c.diag[j].x, isg = c.diag[j].y;
       c128 v;
       if (!transposed) v = cscale(cconj(J[col + (size_t)j * C]), right ? sg * renorm : 1.0);   // V^dag = J^dag
       else v = cscale(cconj(W[col + (size_t)j * ldw]), right ? renorm : isg);                  // S V^dag = W^dag
