@@ -160,18 +160,18 @@ QK_DEV void qk_build_gate_2q(const QkOp& op, const double* x, c128* g) {
   }
 }
 
-// gate of this op, composed with the accumulated gate of its fused group (applied earlier => on the right)
-QK_DEV void qk_build_gate_2q_fused(const QkOp& op, const double* x, c128* g, const c128* gacc) {
+// gate of this op, composed with the accumulated gate of its fused group (applied earlier => on the right);
+// `tmp` is 16 c128 of shared scratch (a local array would cost every thread 256 B of stack)
+QK_DEV void qk_build_gate_2q_fused(const QkOp& op, const double* x, c128* g, const c128* gacc, c128* tmp) {
   qk_build_gate_2q(op, x, g);
   if (op.pad & QK_OPF_ACC) {
-    c128 t[16];
     for (int i = 0; i < 4; ++i)
       for (int j = 0; j < 4; ++j) {
         c128 acc = cmake(0, 0);
         for (int k = 0; k < 4; ++k) cfma(acc, g[i * 4 + k], gacc[k * 4 + j]);
-        t[i * 4 + j] = acc;
+        tmp[i * 4 + j] = acc;
       }
-    for (int i = 0; i < 16; ++i) g[i] = t[i];
+    for (int i = 0; i < 16; ++i) g[i] = tmp[i];
   }
 }
 
@@ -507,9 +507,8 @@ QK_DEV void qk_op_2q(SimCtx& c, const QkOp& op) {
   if (op.pad & QK_OPF_CONT) {   // not the last gate of a fused group: only accumulate its matrix
     QK_PAR_BEGIN(tid)
       if (tid == 0) {
-        c128 g[16];
-        qk_build_gate_2q_fused(op, c.x, g, c.gacc);
-        for (int i = 0; i < 16; ++i) c.gacc[i] = g[i];
+        qk_build_gate_2q_fused(op, c.x, c.gate, c.gacc, (c128*)c.scr);
+        for (int i = 0; i < 16; ++i) c.gacc[i] = c.gate[i];
       }
     QK_PAR_END
     return;
@@ -531,7 +530,7 @@ QK_DEV void qk_op_2q(SimCtx& c, const QkOp& op) {
   QK_PAR_BEGIN(tid)
     for (int i = tid; i < ca * 2 * cb; i += G) As[i] = A[i];
     for (int i = tid; i < cb * 2 * cc; i += G) Bs[i] = B[i];
-    if (tid == 0) qk_build_gate_2q_fused(op, c.x, c.gate, c.gacc);
+    if (tid == 0) qk_build_gate_2q_fused(op, c.x, c.gate, c.gacc, (c128*)c.scr);
   QK_PAR_END
 
   // theta[(a,L),(R,c)] = sum_{l,r} g[(L,R),(l,r)] sum_b A[a,l,b] B[b,r,c]
