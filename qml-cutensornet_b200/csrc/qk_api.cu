@@ -472,7 +472,7 @@ int qk_gram_frags(int device, void* stream_v, int n_qubits, const int32_t* Dx, c
   cudaStream_t stream = (cudaStream_t)stream_v;
 
   int TI = 0, TJ = 0;
-  qk_gram_dmma_tile_shape(&TI, &TJ);
+  qk_gram_dmma_tile_shape(maxD, &TI, &TJ);
   // L2 blocking: CTAs are scheduled in list order, so the pair tiles are emitted supertile by supertile,
   // a supertile being S x S states whose packed bras + kets fit in about half of the 126 MB L2; every state
   // is then fetched from HBM once per supertile instead of once per 8-pair tile.
@@ -552,7 +552,6 @@ int qk_gram_frags(int device, void* stream_v, int n_qubits, const int32_t* Dx, c
   P.tiles = (const int4*)(dbuf + t_off); P.n_cta_tiles = (int)cta.size();
   P.symmetric = symmetric ? 1 : 0;
   P.K = K_dev; P.ldk = ldk; P.slot_x = slot_x; P.slot_y = slot_y;
-  P.skew_ns = getenv("QK_GRAM_SKEW_NS") ? atoi(getenv("QK_GRAM_SKEW_NS")) : 0;
   if (e == cudaSuccess) e = cudaEventCreate(&e0);
   if (e == cudaSuccess) e = cudaEventCreate(&e1);
   if (e == cudaSuccess) e = cudaEventRecord(e0, stream);

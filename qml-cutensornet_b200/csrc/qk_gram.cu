@@ -33,7 +33,6 @@
 #endif
 #define QK_GRAM_WARPS (QK_TI * QK_TJ)
 
-void qk_gram_dmma_tile_shape(int* ti, int* tj) { *ti = QK_TI; *tj = QK_TJ; }
 
 void qk_frag_layout(int n, const int32_t* D, FragLayout* L, int64_t* site_off_bytes) {
   int64_t off = 0;
@@ -291,14 +290,21 @@ __device__ __forceinline__ void qk_site_step(double (&Er)[NT][NT][2], double (&E
 }
 
 // ------------------------------------------------------------------------------------------------
-// DMMA Gram kernel.  NT = max 8x8 tiles per bond (1: D <= 8, 2: D <= 16).
+// DMMA Gram kernel.  NT = max 8x8 tiles per bond (1: D <= 8, 2: D <= 16).  PPW = pairs per warp (one bra,
+// PPW consecutive kets).  CTA tile = QK_TI * PPW kets x QK_TJ bras, 8 warps.
 // ------------------------------------------------------------------------------------------------
+// (PPW = 4 at NT = 1 was measured: 40 % slower -- the extra registers halve the resident CTAs and the four
+// pairs' MMAs serialise in one warp; kept at 1.)
+template <int NT> struct GramCfg { static constexpr int PPW = 1; static constexpr int TI = QK_TI * PPW; };
+
 template <int NT>
-__global__ void __launch_bounds__(QK_GRAM_WARPS * 32, 1) qk_gram_dmma_kernel(const __grid_constant__ GramParams P) {
+__global__ void __launch_bounds__(QK_GRAM_WARPS * 32, NT == 1 ? 4 : 1) qk_gram_dmma_kernel(const __grid_constant__ GramParams P) {
+  constexpr int PPW = GramCfg<NT>::PPW;
+  constexpr int TI = GramCfg<NT>::TI;
   extern __shared__ __align__(128) unsigned char gsm[];
   const int n = P.n;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int stage_bytes = QK_TI * P.slot_x + QK_TJ * P.slot_y;
+  const int stage_bytes = TI * P.slot_x + QK_TJ * P.slot_y;
   unsigned char* stage0 = gsm;
   uint64_t* bars = (uint64_t*)(gsm + (size_t)QK_NS * stage_bytes);   // full[NS], empty[NS]
   int* sDx = (int*)(bars + 2 * QK_NS);
@@ -309,9 +315,9 @@ __global__ void __launch_bounds__(QK_GRAM_WARPS * 32, 1) qk_gram_dmma_kernel(con
   const int y0 = tile.x, x0 = tile.y, y_end = tile.z, x_end = tile.w;
 
   for (int b = threadIdx.x; b <= n; b += blockDim.x) { sDx[b] = P.Dx[b]; sDy[b] = P.Dy[b]; }
-  for (int t = warp; t < QK_TI + QK_TJ; t += QK_GRAM_WARPS) {
-    const bool is_x = t < QK_TI;
-    int idx = is_x ? x0 + t : y0 + (t - QK_TI);
+  for (int t = warp; t < TI + QK_TJ; t += QK_GRAM_WARPS) {
+    const bool is_x = t < TI;
+    int idx = is_x ? x0 + t : y0 + (t - TI);
     const int lim = is_x ? P.Nx : P.Ny;
     if (idx >= lim) idx = lim - 1;
     const unsigned char* src = is_x ? P.fragX + (size_t)idx * P.strideX + P.dataX : P.fragY + (size_t)idx * P.strideY + P.dataY;
@@ -326,7 +332,7 @@ __global__ void __launch_bounds__(QK_GRAM_WARPS * 32, 1) qk_gram_dmma_kernel(con
   }
   __syncthreads();
 
-  // The site blocks of the tile's TI kets and TJ bras are streamed by one elected lane (warp 0, lane 0)
+  // The site blocks of the tile's kets and bras are streamed by one elected lane (warp 0, lane 0)
   // NS-1 sites ahead of the compute; a dedicated producer warp would put 3 warps on one scheduler and
   // cap every thread at 168 registers (16 K registers per scheduler), which the 3M accumulators exceed.
   auto issue_site = [&](int sl) {
@@ -336,18 +342,18 @@ __global__ void __launch_bounds__(QK_GRAM_WARPS * 32, 1) qk_gram_dmma_kernel(con
     const uint32_t bxb = (uint32_t)(sDx[sl] * sDx[sl + 1] * 32);
     const uint32_t byb = (uint32_t)(sDy[sl] * sDy[sl + 1] * 32);
     const uint32_t full = qk_smem_u32(&bars[st]);
-    qk_mbar_expect_tx(full, QK_TI * bxb + QK_TJ * byb);
+    qk_mbar_expect_tx(full, TI * bxb + QK_TJ * byb);
     unsigned char* dst = stage0 + (size_t)st * stage_bytes;
     const int64_t ox = P.offx[sl], oy = P.offy[sl];
 #pragma unroll
-    for (int t = 0; t < QK_TI; ++t) {
+    for (int t = 0; t < TI; ++t) {
       int xi = x0 + t; if (xi >= P.Nx) xi = P.Nx - 1;
       qk_bulk_g2s(qk_smem_u32(dst + (size_t)t * P.slot_x), P.fragX + (size_t)xi * P.strideX + ox, bxb, full);
     }
 #pragma unroll
     for (int t = 0; t < QK_TJ; ++t) {
       int yi = y0 + t; if (yi >= P.Ny) yi = P.Ny - 1;
-      qk_bulk_g2s(qk_smem_u32(dst + (size_t)QK_TI * P.slot_x + (size_t)t * P.slot_y),
+      qk_bulk_g2s(qk_smem_u32(dst + (size_t)TI * P.slot_x + (size_t)t * P.slot_y),
                   P.fragY + (size_t)yi * P.strideY + oy, byb, full);
     }
   };
@@ -355,28 +361,31 @@ __global__ void __launch_bounds__(QK_GRAM_WARPS * 32, 1) qk_gram_dmma_kernel(con
     for (int sl = 0; sl < QK_NS - 1 && sl < n; ++sl) issue_site(sl);
   }
 
-  // ===== one (bra y, ket x) pair per warp =====
-  const int ti = warp % QK_TI, tj = warp / QK_TI;
-  const int x = x0 + ti, y = y0 + tj;
-  const bool active = (x < x_end) && (y < y_end) && (!P.symmetric || x <= y);
-  const unsigned char* tcx = stc + ti * (n + 1);
-  const unsigned char* tcy = stc + (QK_TI + tj) * (n + 1);
-
-  // E[bra tile][ket tile]: real part, imaginary part and their sum (3M complex products)
-  double Er[NT][NT][2], Ei[NT][NT][2], Es[NT][NT][2];
+  // ===== PPW (bra y, ket x) pairs per warp: one bra, PPW consecutive kets =====
+  const int tk = (warp % QK_TI) * PPW, tj = warp / QK_TI;
+  const int y = y0 + tj;
+  bool active[PPW];
+  bool any_active = false;
 #pragma unroll
-  for (int a = 0; a < NT; ++a)
-#pragma unroll
-    for (int b = 0; b < NT; ++b) {
-      Er[a][b][0] = Er[a][b][1] = 0.0; Ei[a][b][0] = Ei[a][b][1] = 0.0; Es[a][b][0] = Es[a][b][1] = 0.0;
-    }
-  if (lane == 0) { Er[0][0][0] = 1.0; Es[0][0][0] = 1.0; }   // E_0 = [1]
+  for (int j = 0; j < PPW; ++j) {
+    const int x = x0 + tk + j;
+    active[j] = (x < x_end) && (y < y_end) && (!P.symmetric || x <= y);
+    any_active = any_active || active[j];
+  }
+  const unsigned char* tcy = stc + (TI + tj) * (n + 1);
 
-  // Two warps share each scheduler's DMMA pipe.  Started together they stay in lockstep (equal work,
-  // alternating MMAs) and reach their non-MMA sections (combines, loads, barrier) at the same time, when
-  // the pipe idles.  Starting the second warp of every scheduler about half a site late lets each
-  // warp's non-MMA section hide under the other's MMAs; the 3-stage pipeline absorbs the skew.
-  if (warp >= QK_GRAM_WARPS / 2 && P.skew_ns > 0) __nanosleep((unsigned)P.skew_ns);
+  // E[pair][bra tile][ket tile]: real part, imaginary part and their sum (3M complex products)
+  double Er[PPW][NT][NT][2], Ei[PPW][NT][NT][2], Es[PPW][NT][NT][2];
+#pragma unroll
+  for (int j = 0; j < PPW; ++j) {
+#pragma unroll
+    for (int a = 0; a < NT; ++a)
+#pragma unroll
+      for (int b = 0; b < NT; ++b) {
+        Er[j][a][b][0] = Er[j][a][b][1] = 0.0; Ei[j][a][b][0] = Ei[j][a][b][1] = 0.0; Es[j][a][b][0] = Es[j][a][b][1] = 0.0;
+      }
+    if (lane == 0) { Er[j][0][0][0] = 1.0; Es[j][0][0][0] = 1.0; }   // E_0 = [1]
+  }
 
   for (int s = 0; s < n; ++s) {
     const int st = s % QK_NS;
@@ -384,51 +393,69 @@ __global__ void __launch_bounds__(QK_GRAM_WARPS * 32, 1) qk_gram_dmma_kernel(con
     if (threadIdx.x == 0 && s + QK_NS - 1 < n) issue_site(s + QK_NS - 1);
     __syncwarp();
     qk_mbar_wait(qk_smem_u32(&bars[st]), par);
-    if (active) {
+    if (any_active) {
       const int KTx = sDx[s] >> 3, MTx = sDx[s + 1] >> 3;
       const int KTy = sDy[s] >> 3, MTy = sDy[s + 1] >> 3;
-      // live k-blocks (of 4) on the contraction side, live 8-tiles on the output side
-      const int kbx = tcx[s], kby = tcy[s];
-      const int mx = (tcx[s + 1] + 1) >> 1, my = (tcy[s + 1] + 1) >> 1, ky = (kby + 1) >> 1;
+      const int kby = tcy[s], my = (tcy[s + 1] + 1) >> 1, ky = (kby + 1) >> 1;
       const unsigned char* sb = stage0 + (size_t)st * stage_bytes;
-      const double2* bx = (const double2*)(sb + (size_t)ti * P.slot_x);
-      const double2* by = (const double2*)(sb + (size_t)QK_TI * P.slot_x + (size_t)tj * P.slot_y);
-      // common case in the bulk of the chain: all tiles live, k-block counts 2NT or 2NT-1
-      const bool full = (mx == NT) && (my == NT) && (kbx >= 2 * NT - 1) && (kby >= 2 * NT - 1) &&
-                        (MTx == NT) && (KTx == NT) && (MTy == NT) && (KTy == NT);
-      if (full) {
-        if (kbx == 2 * NT) {
-          if (kby == 2 * NT) qk_site_step<NT, true, 2 * NT, 2 * NT>(Er, Ei, Es, bx, by, lane, 0, 0, 0, 0, 0, 0, 0, 0, 0);
-          else qk_site_step<NT, true, 2 * NT, 2 * NT - 1>(Er, Ei, Es, bx, by, lane, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+      const double2* by = (const double2*)(sb + (size_t)TI * P.slot_x + (size_t)tj * P.slot_y);
+      const bool lay_full = (MTx == NT) && (KTx == NT) && (MTy == NT) && (KTy == NT);
+#pragma unroll
+      for (int j = 0; j < PPW; ++j) {
+        if (!active[j]) continue;
+        const unsigned char* tcx = stc + (tk + j) * (n + 1);
+        // live k-blocks (of 4) on the contraction side, live 8-tiles on the output side
+        const int kbx = tcx[s], mx = (tcx[s + 1] + 1) >> 1;
+        const double2* bx = (const double2*)(sb + (size_t)(tk + j) * P.slot_x);
+        // common case in the bulk of the chain: all tiles live, k-block counts 2NT or 2NT-1
+        const bool full = lay_full && (mx == NT) && (my == NT) && (kbx >= 2 * NT - 1) && (kby >= 2 * NT - 1);
+        if (full) {
+          if (kbx == 2 * NT) {
+            if (kby == 2 * NT) qk_site_step<NT, true, 2 * NT, 2 * NT>(Er[j], Ei[j], Es[j], bx, by, lane, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+            else qk_site_step<NT, true, 2 * NT, 2 * NT - 1>(Er[j], Ei[j], Es[j], bx, by, lane, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+          } else {
+            if (kby == 2 * NT) qk_site_step<NT, true, 2 * NT - 1, 2 * NT>(Er[j], Ei[j], Es[j], bx, by, lane, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+            else qk_site_step<NT, true, 2 * NT - 1, 2 * NT - 1>(Er[j], Ei[j], Es[j], bx, by, lane, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+          }
         } else {
-          if (kby == 2 * NT) qk_site_step<NT, true, 2 * NT - 1, 2 * NT>(Er, Ei, Es, bx, by, lane, 0, 0, 0, 0, 0, 0, 0, 0, 0);
-          else qk_site_step<NT, true, 2 * NT - 1, 2 * NT - 1>(Er, Ei, Es, bx, by, lane, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+          qk_site_step<NT, false, 0, 0>(Er[j], Ei[j], Es[j], bx, by, lane, MTx, KTx, MTy, KTy, mx, my, ky, kbx, kby);
         }
-      } else {
-        qk_site_step<NT, false, 0, 0>(Er, Ei, Es, bx, by, lane, MTx, KTx, MTy, KTy, mx, my, ky, kbx, kby);
       }
     }
     __syncwarp();
     if (lane == 0) qk_mbar_arrive(qk_smem_u32(&bars[QK_NS + st]));
   }
-  if (active && lane == 0) {
-    const double v = Er[0][0][0] * Er[0][0][0] + Ei[0][0][0] * Ei[0][0][0];
-    P.K[(size_t)y * P.ldk + x] = v;
-    if (P.symmetric) P.K[(size_t)x * P.ldk + y] = v;
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < PPW; ++j) {
+      if (!active[j]) continue;
+      const int x = x0 + tk + j;
+      const double v = Er[j][0][0][0] * Er[j][0][0][0] + Ei[j][0][0][0] * Ei[j][0][0][0];
+      P.K[(size_t)y * P.ldk + x] = v;
+      if (P.symmetric) P.K[(size_t)x * P.ldk + y] = v;
+    }
   }
 }
 
+// CTA tile shape (kets x bras) of the tensor-core kernel for a given maximum padded bond dimension
+void qk_gram_dmma_tile_shape(int maxD, int* ti, int* tj) {
+  *ti = (maxD <= 8) ? GramCfg<1>::TI : GramCfg<2>::TI;
+  *tj = QK_TJ;
+}
+
+template <int NT>
 static size_t gram_smem_bytes(const GramParams& P) {
-  size_t b = (size_t)QK_NS * (QK_TI * (size_t)P.slot_x + QK_TJ * (size_t)P.slot_y);
+  constexpr int TI = GramCfg<NT>::TI;
+  size_t b = (size_t)QK_NS * (TI * (size_t)P.slot_x + QK_TJ * (size_t)P.slot_y);
   b += 2 * QK_NS * sizeof(uint64_t);
   b += 2 * (size_t)(P.n + 1) * sizeof(int);
-  b += (size_t)(QK_TI + QK_TJ) * (P.n + 1);
+  b += (size_t)(TI + QK_TJ) * (P.n + 1);
   return (b + 127) & ~(size_t)127;
 }
 
 template <int NT>
 static cudaError_t launch_gram_nt(const GramParams& P, cudaStream_t stream) {
-  const size_t smem = gram_smem_bytes(P);
+  const size_t smem = gram_smem_bytes<NT>(P);
   cudaError_t e = cudaFuncSetAttribute(qk_gram_dmma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   qk_gram_dmma_kernel<NT><<<P.n_cta_tiles, QK_GRAM_WARPS * 32, smem, stream>>>(P);

@@ -42,11 +42,10 @@ struct GramParams {
   double* K;
   int64_t ldk;
   int slot_x, slot_y;       // bytes reserved per state per pipeline stage
-  int skew_ns;              // start-up delay of the second warp of every scheduler (see qk_gram.cu)
 };
 // DMMA + bulk-copy pipeline kernel; requires max(D) <= 16.
 cudaError_t qk_launch_gram_dmma(const GramParams& P, int maxD, cudaStream_t stream);
-void qk_gram_dmma_tile_shape(int* ti, int* tj);
+void qk_gram_dmma_tile_shape(int maxD, int* ti, int* tj);
 // CUDA-core kernel on the same frag buffers, any padded D <= 32 (one CTA per listed (y, x) pair)
 cudaError_t qk_launch_gram_frag_generic(const GramParams& P, const int2* pairs_dev, int n_pairs, int maxD,
                                         cudaStream_t stream);
