@@ -149,66 +149,50 @@ __device__ __forceinline__ void qk_dmma_z(double (&acc)[2], double a, double b) 
 
 // ------------------------------------------------------------------------------------------------
 // One site of the transfer sweep for one (bra, ket) pair, E kept in accumulator fragments.
-//   STATIC = true : every 8-tile of the four bonds involved is live and the live k-block counts are
-//                   the compile-time KBX / KBY -> straight-line code, no predicate around any MMA.
-//                   (ptxas paces DMMAs with static stall counts and guards every predicated
-//                   mma.sync with WARPSYNC + NOPs, so a predicated-off MMA costs as much as a real one.)
-//   STATIC = false: generic path, live tiles / k-blocks from the per-state trailer bytes.
+// The live 8-tiles of the four bonds involved are compile-time:
+//   KX / MX = live tiles of the ket's left / right bond, KY / MY = same for the bra;
+// the live k-blocks (of 4) are kbx in {2KX-1, 2KX}, kby in {2KY-1, 2KY}: the last k-block of each
+// step sits behind one warp-uniform branch, everything else is straight-line code with no predicate
+// around any MMA.  (ptxas paces DMMAs with static stall counts and guards every predicated mma.sync
+// with WARPSYNC + NOPs, so a predicated-off MMA costs as much as a real one: a version that predicated
+// dead tiles away spent the time of the full 16x16 problem on every site.)
+// Layout tile counts (MTx, KTx, MTy, KTy = padded D / 8) only enter the operand addresses.
 // ------------------------------------------------------------------------------------------------
-template <int NT, bool STATIC, int KBX, int KBY>
+template <int NT, int KX, int MX, int KY, int MY>
 __device__ __forceinline__ void qk_site_step(double (&Er)[NT][NT][2], double (&Ei)[NT][NT][2], double (&Es)[NT][NT][2],
                                              const double2* __restrict__ bx, const double2* __restrict__ by, int lane,
-                                             int MTx_r, int KTx_r, int MTy_r, int KTy_r, int mx_r, int my_r, int ky_r,
-                                             int kbx_r, int kby_r) {
-  const int MTx = STATIC ? NT : MTx_r, KTx = STATIC ? NT : KTx_r, MTy = STATIC ? NT : MTy_r, KTy = STATIC ? NT : KTy_r;
-  const int mx = STATIC ? NT : mx_r, my = STATIC ? NT : my_r, ky = STATIC ? NT : ky_r;
-  const int kbx = STATIC ? KBX : kbx_r, kby = STATIC ? KBY : kby_r;
+                                             int MTx, int KTx, int MTy, int KTy, bool last_x, bool last_y) {
   // Both physical indices p are carried together: all step-1 MMAs (p = 0, 1), one combine, all step-2
   // MMAs, one combine -- two MMA -> DADD -> MMA dependency bubbles per site instead of four, and long
   // uninterrupted MMA phases that the sibling warp on the scheduler can interleave with.
-  double T1[2][NT][NT][2], T2[2][NT][NT][2], T3[2][NT][NT][2];   // T^T[p][ket-right tile][bra-left tile]
-  if (!STATIC) {   // the static path starts every accumulator chain with a zero-input MMA instead
-#pragma unroll
-    for (int p = 0; p < 2; ++p)
-#pragma unroll
-      for (int a = 0; a < NT; ++a)
-#pragma unroll
-        for (int b = 0; b < NT; ++b) {
-          T1[p][a][b][0] = T1[p][a][b][1] = 0.0; T2[p][a][b][0] = T2[p][a][b][1] = 0.0; T3[p][a][b][0] = T3[p][a][b][1] = 0.0;
-        }
-  }
+  double T1[2][MX][KY][2], T2[2][MX][KY][2], T3[2][MX][KY][2];   // T^T[p][ket-right tile][bra-left tile]
   // step 1: T_p^T[c'][a] += sum_c A_x[c,p,c'] * E[a][c]   (S1 = Ar Er, S2 = Ai Ei, S3 = (Ar+Ai)(Er+Ei));
-  // k-block outermost: 6*mx*ky independent accumulators between two MMAs on the same one.
+  // k-block outermost: 6*MX*KY independent accumulators between two MMAs on the same one.
+  const double2* px = bx + lane;
+  const int sx_mt = KTx * 64, sx_p = MTx * sx_mt;
 #pragma unroll
-  for (int kt = 0; kt < NT; ++kt) {
+  for (int kb = 0; kb < 2 * KX; ++kb) {
+    const int kt = kb >> 1, e = kb & 1;
+    if (kb < 2 * KX - 1 || last_x) {
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      if (2 * kt + e < kbx) {
+      for (int p = 0; p < 2; ++p) {
 #pragma unroll
-        for (int p = 0; p < 2; ++p) {
+        for (int mt = 0; mt < MX; ++mt) {
+          const double2* f = px + p * sx_p + mt * sx_mt + kt * 64;
+          const double2 fr = f[0], fm = f[32];
+          const double ar = e ? fr.y : fr.x;
+          const double ai = e ? fm.y : fm.x;
+          const double as = ar + ai;
 #pragma unroll
-          for (int mt = 0; mt < NT; ++mt) {
-            if (mt < mx) {
-              const int mtc = mt < MTx ? mt : MTx - 1, ktc = kt < KTx ? kt : KTx - 1;
-              const int fi = (((p * MTx + mtc) * KTx + ktc) * 2) * 32 + lane;
-              const double2 fr = bx[fi], fm = bx[fi + 32];
-              const double ar = e ? fr.y : fr.x;
-              const double ai = e ? fm.y : fm.x;
-              const double as = ar + ai;
-#pragma unroll
-              for (int at = 0; at < NT; ++at) {
-                if (at < ky) {
-                  if (STATIC && kt == 0 && e == 0) {
-                    qk_dmma_z(T1[p][mt][at], ar, Er[at][kt][e]);
-                    qk_dmma_z(T2[p][mt][at], ai, Ei[at][kt][e]);
-                    qk_dmma_z(T3[p][mt][at], as, Es[at][kt][e]);
-                  } else {
-                    qk_dmma(T1[p][mt][at], ar, Er[at][kt][e]);
-                    qk_dmma(T2[p][mt][at], ai, Ei[at][kt][e]);
-                    qk_dmma(T3[p][mt][at], as, Es[at][kt][e]);
-                  }
-                }
-              }
+          for (int at = 0; at < KY; ++at) {
+            if (kb == 0) {   // first MMA of a chain: zero accumulator input, no register zero-fill
+              qk_dmma_z(T1[p][mt][at], ar, Er[at][kt][e]);
+              qk_dmma_z(T2[p][mt][at], ai, Ei[at][kt][e]);
+              qk_dmma_z(T3[p][mt][at], as, Es[at][kt][e]);
+            } else {
+              qk_dmma(T1[p][mt][at], ar, Er[at][kt][e]);
+              qk_dmma(T2[p][mt][at], ai, Ei[at][kt][e]);
+              qk_dmma(T3[p][mt][at], as, Es[at][kt][e]);
             }
           }
         }
@@ -219,9 +203,9 @@ __device__ __forceinline__ void qk_site_step(double (&Er)[NT][NT][2], double (&E
 #pragma unroll
   for (int p = 0; p < 2; ++p)
 #pragma unroll
-    for (int a = 0; a < NT; ++a)
+    for (int a = 0; a < MX; ++a)
 #pragma unroll
-      for (int b = 0; b < NT; ++b)
+      for (int b = 0; b < KY; ++b)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const double u1 = T1[p][a][b][e], u2 = T2[p][a][b][e], u3 = T3[p][a][b][e];
@@ -230,56 +214,43 @@ __device__ __forceinline__ void qk_site_step(double (&Er)[NT][NT][2], double (&E
           T3[p][a][b][e] = u3 - 2.0 * u2;
         }
   // step 2: E'[b'][c'] += sum_{a,p} conj(A_y[a,p,b']) * T_p[a][c']:  S1 = Ar Tr, S2 = Ai Ti, S3 = (Ar-Ai)(Tr+Ti)
-  double F1[NT][NT][2], F2[NT][NT][2], F3[NT][NT][2];
-  if (!STATIC) {
+  double F1[MY][MX][2], F2[MY][MX][2], F3[MY][MX][2];
+  const double2* py = by + lane;
+  const int sy_mt = KTy * 64, sy_p = MTy * sy_mt;
 #pragma unroll
-    for (int a = 0; a < NT; ++a)
+  for (int kb = 0; kb < 2 * KY; ++kb) {
+    const int at = kb >> 1, e = kb & 1;
+    if (kb < 2 * KY - 1 || last_y) {
 #pragma unroll
-      for (int b = 0; b < NT; ++b) {
-        F1[a][b][0] = F1[a][b][1] = 0.0; F2[a][b][0] = F2[a][b][1] = 0.0; F3[a][b][0] = F3[a][b][1] = 0.0;
-      }
-  }
+      for (int p = 0; p < 2; ++p) {
 #pragma unroll
-  for (int at = 0; at < NT; ++at) {
+        for (int bt = 0; bt < MY; ++bt) {
+          const double2* f = py + p * sy_p + bt * sy_mt + at * 64;
+          const double2 fr = f[0], fm = f[32];
+          const double ar = e ? fr.y : fr.x;
+          const double ai = e ? fm.y : fm.x;
+          const double ad = ar - ai;
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      if (2 * at + e < kby) {
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-#pragma unroll
-          for (int bt = 0; bt < NT; ++bt) {
-            if (bt < my) {
-              const int btc = bt < MTy ? bt : MTy - 1, atc = at < KTy ? at : KTy - 1;
-              const int fi = (((p * MTy + btc) * KTy + atc) * 2) * 32 + lane;
-              const double2 fr = by[fi], fm = by[fi + 32];
-              const double ar = e ? fr.y : fr.x;
-              const double ai = e ? fm.y : fm.x;
-              const double ad = ar - ai;
-#pragma unroll
-              for (int ct = 0; ct < NT; ++ct) {
-                if (ct < mx) {
-                  if (STATIC && at == 0 && e == 0 && p == 0) {
-                    qk_dmma_z(F1[bt][ct], ar, T1[p][ct][at][e]);
-                    qk_dmma_z(F2[bt][ct], ai, T2[p][ct][at][e]);
-                    qk_dmma_z(F3[bt][ct], ad, T3[p][ct][at][e]);
-                  } else {
-                    qk_dmma(F1[bt][ct], ar, T1[p][ct][at][e]);
-                    qk_dmma(F2[bt][ct], ai, T2[p][ct][at][e]);
-                    qk_dmma(F3[bt][ct], ad, T3[p][ct][at][e]);
-                  }
-                }
-              }
+          for (int ct = 0; ct < MX; ++ct) {
+            if (kb == 0 && p == 0) {
+              qk_dmma_z(F1[bt][ct], ar, T1[p][ct][at][e]);
+              qk_dmma_z(F2[bt][ct], ai, T2[p][ct][at][e]);
+              qk_dmma_z(F3[bt][ct], ad, T3[p][ct][at][e]);
+            } else {
+              qk_dmma(F1[bt][ct], ar, T1[p][ct][at][e]);
+              qk_dmma(F2[bt][ct], ai, T2[p][ct][at][e]);
+              qk_dmma(F3[bt][ct], ad, T3[p][ct][at][e]);
             }
           }
         }
       }
     }
   }
-  // E' = (S1 + S2) + i (S3 - S1 + S2)
+  // E' = (S1 + S2) + i (S3 - S1 + S2); tiles outside MY x MX are not read by the next site
 #pragma unroll
-  for (int a = 0; a < NT; ++a)
+  for (int a = 0; a < MY; ++a)
 #pragma unroll
-    for (int b = 0; b < NT; ++b)
+    for (int b = 0; b < MX; ++b)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const double u1 = F1[a][b][e], u2 = F2[a][b][e], u3 = F3[a][b][e];
@@ -287,6 +258,29 @@ __device__ __forceinline__ void qk_site_step(double (&Er)[NT][NT][2], double (&E
         Ei[a][b][e] = u3 - u1 + u2;
         Es[a][b][e] = u3 + 2.0 * u2;
       }
+}
+
+// dispatch on the live tile counts (all warp-uniform)
+template <int NT>
+__device__ __forceinline__ void qk_site_dispatch(double (&Er)[NT][NT][2], double (&Ei)[NT][NT][2], double (&Es)[NT][NT][2],
+                                                 const double2* __restrict__ bx, const double2* __restrict__ by, int lane,
+                                                 int MTx, int KTx, int MTy, int KTy, int kbx, int mx, int kby, int my) {
+  const bool last_x = !(kbx & 1), last_y = !(kby & 1);
+  if constexpr (NT == 1) {
+    qk_site_step<1, 1, 1, 1, 1>(Er, Ei, Es, bx, by, lane, MTx, KTx, MTy, KTy, last_x, last_y);
+  } else {
+    const int kx = (kbx + 1) >> 1, ky = (kby + 1) >> 1;
+    const int v = (kx - 1) | ((mx - 1) << 1) | ((ky - 1) << 2) | ((my - 1) << 3);
+#define QK_SITE_CASE(V) \
+    case V: qk_site_step<2, 1 + ((V) & 1), 1 + (((V) >> 1) & 1), 1 + (((V) >> 2) & 1), 1 + (((V) >> 3) & 1)>( \
+                Er, Ei, Es, bx, by, lane, MTx, KTx, MTy, KTy, last_x, last_y); break;
+    switch (v) {
+      QK_SITE_CASE(0) QK_SITE_CASE(1) QK_SITE_CASE(2) QK_SITE_CASE(3) QK_SITE_CASE(4) QK_SITE_CASE(5) QK_SITE_CASE(6) QK_SITE_CASE(7)
+      QK_SITE_CASE(8) QK_SITE_CASE(9) QK_SITE_CASE(10) QK_SITE_CASE(11) QK_SITE_CASE(12) QK_SITE_CASE(13) QK_SITE_CASE(14)
+      default: qk_site_step<2, 2, 2, 2, 2>(Er, Ei, Es, bx, by, lane, MTx, KTx, MTy, KTy, last_x, last_y); break;
+    }
+#undef QK_SITE_CASE
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -396,30 +390,17 @@ __global__ void __launch_bounds__(QK_GRAM_WARPS * 32, NT == 1 ? 4 : 1) qk_gram_d
     if (any_active) {
       const int KTx = sDx[s] >> 3, MTx = sDx[s + 1] >> 3;
       const int KTy = sDy[s] >> 3, MTy = sDy[s + 1] >> 3;
-      const int kby = tcy[s], my = (tcy[s + 1] + 1) >> 1, ky = (kby + 1) >> 1;
+      // live k-blocks (of 4) on the contraction side, live 8-tiles on the output side
+      const int kby = tcy[s], my = (tcy[s + 1] + 1) >> 1;
       const unsigned char* sb = stage0 + (size_t)st * stage_bytes;
       const double2* by = (const double2*)(sb + (size_t)TI * P.slot_x + (size_t)tj * P.slot_y);
-      const bool lay_full = (MTx == NT) && (KTx == NT) && (MTy == NT) && (KTy == NT);
 #pragma unroll
       for (int j = 0; j < PPW; ++j) {
         if (!active[j]) continue;
         const unsigned char* tcx = stc + (tk + j) * (n + 1);
-        // live k-blocks (of 4) on the contraction side, live 8-tiles on the output side
         const int kbx = tcx[s], mx = (tcx[s + 1] + 1) >> 1;
         const double2* bx = (const double2*)(sb + (size_t)(tk + j) * P.slot_x);
-        // common case in the bulk of the chain: all tiles live, k-block counts 2NT or 2NT-1
-        const bool full = lay_full && (mx == NT) && (my == NT) && (kbx >= 2 * NT - 1) && (kby >= 2 * NT - 1);
-        if (full) {
-          if (kbx == 2 * NT) {
-            if (kby == 2 * NT) qk_site_step<NT, true, 2 * NT, 2 * NT>(Er[j], Ei[j], Es[j], bx, by, lane, 0, 0, 0, 0, 0, 0, 0, 0, 0);
-            else qk_site_step<NT, true, 2 * NT, 2 * NT - 1>(Er[j], Ei[j], Es[j], bx, by, lane, 0, 0, 0, 0, 0, 0, 0, 0, 0);
-          } else {
-            if (kby == 2 * NT) qk_site_step<NT, true, 2 * NT - 1, 2 * NT>(Er[j], Ei[j], Es[j], bx, by, lane, 0, 0, 0, 0, 0, 0, 0, 0, 0);
-            else qk_site_step<NT, true, 2 * NT - 1, 2 * NT - 1>(Er[j], Ei[j], Es[j], bx, by, lane, 0, 0, 0, 0, 0, 0, 0, 0, 0);
-          }
-        } else {
-          qk_site_step<NT, false, 0, 0>(Er[j], Ei[j], Es[j], bx, by, lane, MTx, KTx, MTy, KTy, mx, my, ky, kbx, kby);
-        }
+        qk_site_dispatch<NT>(Er[j], Ei[j], Es[j], bx, by, lane, MTx, KTx, MTy, KTy, kbx, mx, kby, my);
       }
     }
     __syncwarp();
