@@ -317,22 +317,32 @@ __global__ void __launch_bounds__(QK_GRAM_WARPS * 32, NT == 1 ? 4 : 1) qk_gram_d
     const unsigned char* src = is_x ? P.fragX + (size_t)idx * P.strideX + P.dataX : P.fragY + (size_t)idx * P.strideY + P.dataY;
     for (int b = lane; b <= n; b += 32) stc[t * (n + 1) + b] = src[b];
   }
+  int* cnt = (int*)(bars + QK_NS);                                   // consumer counters, one per stage
+  __shared__ int s_weight[TI];
   if (threadIdx.x == 0) {
     for (int s = 0; s < QK_NS; ++s) {
       qk_mbar_init(qk_smem_u32(&bars[s]), 1);                       // full: the issuing lane's expect_tx arrive
-      qk_mbar_init(qk_smem_u32(&bars[QK_NS + s]), QK_GRAM_WARPS);   // empty: one arrive per warp
+      cnt[s] = 0;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  // weight of every ket of the tile (sum of squared live k-block counts) for the warp -> pair assignment below
+  if (warp < TI) {
+    int w = 0;
+    for (int b = lane; b <= n; b += 32) { const int k = stc[warp * (n + 1) + b]; w += k * k; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    if (lane == 0) s_weight[warp] = w;
+  }
+  __syncthreads();
 
-  // The site blocks of the tile's kets and bras are streamed by one elected lane (warp 0, lane 0)
-  // NS-1 sites ahead of the compute; a dedicated producer warp would put 3 warps on one scheduler and
-  // cap every thread at 168 registers (16 K registers per scheduler), which the 3M accumulators exceed.
+  // The site blocks of the tile's kets and bras are streamed with cp.async.bulk, NS sites deep.  There is no
+  // producer warp (3 warps on one scheduler would cap every thread at 168 registers, which the 3M accumulators
+  // exceed) and no empty barrier: the warp that is LAST to finish a site (shared-memory counter) refills that
+  // stage with site s + NS at once, so a fast warp is never held back by issuing loads for the slow ones.
   auto issue_site = [&](int sl) {
     const int st = sl % QK_NS;
-    const uint32_t par = (uint32_t)((sl / QK_NS) & 1);
-    qk_mbar_wait(qk_smem_u32(&bars[QK_NS + st]), par ^ 1u);     // all warps released the previous use
     const uint32_t bxb = (uint32_t)(sDx[sl] * sDx[sl + 1] * 32);
     const uint32_t byb = (uint32_t)(sDy[sl] * sDy[sl + 1] * 32);
     const uint32_t full = qk_smem_u32(&bars[st]);
@@ -352,11 +362,24 @@ __global__ void __launch_bounds__(QK_GRAM_WARPS * 32, NT == 1 ? 4 : 1) qk_gram_d
     }
   };
   if (threadIdx.x == 0) {
-    for (int sl = 0; sl < QK_NS - 1 && sl < n; ++sl) issue_site(sl);
+    for (int sl = 0; sl < QK_NS && sl < n; ++sl) issue_site(sl);
   }
 
   // ===== PPW (bra y, ket x) pairs per warp: one bra, PPW consecutive kets =====
-  const int tk = (warp % QK_TI) * PPW, tj = warp / QK_TI;
+  // Warps q and q + 4 share a scheduler.  Its two pairs are (r-th lightest ket, bra 0) and (r-th heaviest ket,
+  // bra 1), so the four schedulers of the SM carry about the same number of MMAs.
+  const int tj = warp / QK_TI;
+  int tk = (warp % QK_TI) * PPW;
+  if (PPW == 1) {
+    const int want = (tj & 1) ? QK_TI - 1 - (warp % QK_TI) : (warp % QK_TI);
+#pragma unroll
+    for (int t = 0; t < QK_TI; ++t) {
+      int rank = 0;
+#pragma unroll
+      for (int u = 0; u < QK_TI; ++u) rank += (s_weight[u] < s_weight[t]) || (s_weight[u] == s_weight[t] && u < t);
+      if (rank == want) tk = t;
+    }
+  }
   const int y = y0 + tj;
   bool active[PPW];
   bool any_active = false;
@@ -384,8 +407,6 @@ __global__ void __launch_bounds__(QK_GRAM_WARPS * 32, NT == 1 ? 4 : 1) qk_gram_d
   for (int s = 0; s < n; ++s) {
     const int st = s % QK_NS;
     const uint32_t par = (uint32_t)((s / QK_NS) & 1);
-    if (threadIdx.x == 0 && s + QK_NS - 1 < n) issue_site(s + QK_NS - 1);
-    __syncwarp();
     qk_mbar_wait(qk_smem_u32(&bars[st]), par);
     if (any_active) {
       const int KTx = sDx[s] >> 3, MTx = sDx[s + 1] >> 3;
@@ -404,7 +425,14 @@ __global__ void __launch_bounds__(QK_GRAM_WARPS * 32, NT == 1 ? 4 : 1) qk_gram_d
       }
     }
     __syncwarp();
-    if (lane == 0) qk_mbar_arrive(qk_smem_u32(&bars[QK_NS + st]));
+    if (lane == 0) {
+      __threadfence_block();                                   // this warp's reads of the stage are done
+      if (atomicAdd(&cnt[st], 1) == QK_GRAM_WARPS - 1) {       // last warp out refills the stage
+        cnt[st] = 0;
+        __threadfence_block();
+        if (s + QK_NS < n) issue_site(s + QK_NS);
+      }
+    }
   }
   if (lane == 0) {
 #pragma unroll
