@@ -57,11 +57,12 @@ struct SimShared {
 
 struct SimCtx {
   const SimParams* P;
-  c128* W;        // region 1: working matrix (column-major)
-  c128* J;        // region 2: staging for site tensors / accumulated rotations / Q
+  c128* W;        // working matrix (column-major), rmax^2 entries; its tail doubles as staging
+  c128* ef;       // [4*G] tile of the gate-folded half contraction (qk_op_2q)
   double* scr;    // 4*G doubles reduction scratch
   double* nrm2;   // [rmax]
   int* order;     // [rmax]
+  int* swp;       // [rmax] column swaps that compact the kept columns
   c128* gate;     // [16]
   c128* gacc;     // [16] product of the gates of a fused group so far
   c128* diag;     // [rmax] diagonal of R (Householder)
@@ -74,14 +75,15 @@ struct SimCtx {
 // bytes of shared memory the core needs for group size G
 QK_HD size_t qk_sim_smem_bytes(int n, int rmax, int G) {
   size_t wr = (size_t)rmax * rmax;
-  size_t b = 2 * wr * sizeof(c128);         // W, J
+  size_t b = wr * sizeof(c128);             // W
+  b += (size_t)4 * G * sizeof(c128);        // ef
   b += (size_t)QK_SCR_PER_THREAD * G * sizeof(double);   // scr
   b += (size_t)rmax * sizeof(double);       // nrm2
   b += 32 * sizeof(c128);                   // gate + fused-gate accumulator
   b += (size_t)rmax * sizeof(c128);         // diag
   b += (size_t)(n + 1) * sizeof(double);    // x (+pad)
   b += sizeof(SimShared);
-  b += (size_t)rmax * sizeof(int);          // order
+  b += (size_t)2 * rmax * sizeof(int);      // order, swp
   b += (size_t)(n + 1) * sizeof(int);       // chi
   return (b + 15) & ~(size_t)15;
 }
@@ -90,8 +92,8 @@ QK_DEV void qk_sim_carve(SimCtx& c, const SimParams* P, unsigned char* smem, int
   const size_t wr = (size_t)P->rmax * P->rmax;
   c.P = P;
   c.W = (c128*)smem;
-  c.J = c.W + wr;
-  c.scr = (double*)(c.J + wr);
+  c.ef = c.W + wr;
+  c.scr = (double*)(c.ef + 4 * G);
   c.nrm2 = c.scr + QK_SCR_PER_THREAD * G;
   c.gate = (c128*)(c.nrm2 + P->rmax + (P->rmax & 1));
   c.gacc = c.gate + 16;
@@ -99,7 +101,8 @@ QK_DEV void qk_sim_carve(SimCtx& c, const SimParams* P, unsigned char* smem, int
   c.x = (double*)(c.diag + P->rmax);
   c.sh = (SimShared*)(c.x + P->n + (P->n & 1));
   c.order = (int*)(c.sh + 1);
-  c.chi = c.order + P->rmax;
+  c.swp = c.order + P->rmax;
+  c.chi = c.swp + P->rmax;
 }
 
 QK_DEV c128* qk_site(const SimCtx& c, int s) { return c.state + c.P->site_off[s]; }
@@ -176,8 +179,11 @@ QK_DEV void qk_build_gate_2q_fused(const QkOp& op, const double* x, c128* g, con
 }
 
 // ------------------------------------------------------------------------------------------------
-// one-sided Jacobi (Hestenes) on the R x C matrix W (column-major, ld = R); J (C x C) accumulates
-// the rotations:  W_out = W_in * J,  J unitary.  At convergence the columns of W are orthogonal.
+// one-sided Jacobi (Hestenes) on the R x C matrix W (column-major, ld = R):  W_out = W_in * V, V unitary.
+// At convergence the columns of W are orthogonal (= U Sigma).  V is NOT accumulated: a second C x C matrix
+// would double the shared memory per datapoint (and with it halve the datapoints resident per SM) and the
+// rotations applied to it are a third of the work of a round; qk_op_2q recovers the factor it needs from
+// W_out^dag W_in = Sigma^2 V^dag through a half contraction with the site tensors instead.
 // ------------------------------------------------------------------------------------------------
 QK_DEV bool qk_rr_pair(int i, int r, int Ce, int C, int& p, int& q) {
   // round-robin tournament: Ce (even) players, round r in [0, Ce-1), pair slot i in [0, Ce/2)
@@ -255,9 +261,8 @@ QK_DEV void qk_rotate_rows(c128* up, c128* uq, int rows, int sl, int tpp, double
 // Device fast path of one (pair, round) step: the thread's <= RPT rows of both columns stay in
 // registers between the dot products and the rotation; partial sums reduced with warp shuffles.
 template <int RPT>
-__device__ __forceinline__ void qk_pair_step(c128* __restrict__ wp, c128* __restrict__ wq, c128* __restrict__ jp,
-                                             c128* __restrict__ jq, int R, int C, int sl, int tpp, bool valid,
-                                             double tol2, double floor2, double abs2, int* rotated) {
+__device__ __forceinline__ void qk_pair_step(c128* __restrict__ wp, c128* __restrict__ wq, int R, int sl, int tpp,
+                                             bool valid, double tol2, double floor2, double abs2, int* rotated) {
   c128 xp[RPT], xq[RPT];
   double a = 0, b = 0, gr = 0, gi = 0;
 #pragma unroll
@@ -288,24 +293,13 @@ __device__ __forceinline__ void qk_pair_step(c128* __restrict__ wp, c128* __rest
         wq[row] = xq[k];
       }
     }
-#pragma unroll
-    for (int k = 0; k < RPT; ++k) {     // C <= R, so the accumulated rotations need <= RPT rows too
-      const int row = sl + k * tpp;
-      if (row < C) {
-        c128 yp = jp[row], yq = jq[row];
-        qk_rot2(yp, yq, cs, f);
-        jp[row] = yp;
-        jq[row] = yq;
-      }
-    }
     if (sl == 0 && rot == 2) *rotated = 1;
   }
 }
 
 // Same step for any number of rows per thread (rows are re-read for the rotation).
-__device__ __forceinline__ void qk_pair_step_generic(c128* wp, c128* wq, c128* jp, c128* jq, int R, int C, int sl,
-                                                     int tpp, bool valid, double tol2, double floor2, double abs2,
-                                                     int* rotated) {
+__device__ __forceinline__ void qk_pair_step_generic(c128* wp, c128* wq, int R, int sl, int tpp, bool valid,
+                                                     double tol2, double floor2, double abs2, int* rotated) {
   double a = 0, b = 0, gr = 0, gi = 0;
   if (valid) {
     for (int row = sl; row < R; row += tpp) {
@@ -326,7 +320,6 @@ __device__ __forceinline__ void qk_pair_step_generic(c128* wp, c128* wq, c128* j
   const int rot = valid ? qk_rotation(a, b, gr, gi, tol2, floor2, abs2, cs, f) : 0;
   if (rot) {
     qk_rotate_rows(wp, wq, R, sl, tpp, cs, f);
-    qk_rotate_rows(jp, jq, C, sl, tpp, cs, f);
     if (sl == 0 && rot == 2) *rotated = 1;
   }
 }
@@ -335,7 +328,6 @@ __device__ __forceinline__ void qk_pair_step_generic(c128* wp, c128* wq, c128* j
 template <int G>
 QK_DEV void qk_jacobi(SimCtx& c, int R, int C) {
   c128* W = c.W;
-  c128* J = c.J;
   const int ldw = R;
   const int Ce = (C + 1) & ~1;
   const int npairs = Ce / 2;
@@ -375,13 +367,11 @@ QK_DEV void qk_jacobi(SimCtx& c, int R, int C) {
             const bool valid = (i < npairs) && qk_rr_pair(i, r, Ce, C, p, q);
             c128* wp = W + (size_t)p * ldw;
             c128* wq = W + (size_t)q * ldw;
-            c128* jp = J + (size_t)p * C;
-            c128* jq = J + (size_t)q * C;
-            if (rpt <= 1) qk_pair_step<1>(wp, wq, jp, jq, R, C, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
-            else if (rpt <= 2) qk_pair_step<2>(wp, wq, jp, jq, R, C, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
-            else if (rpt <= 4) qk_pair_step<4>(wp, wq, jp, jq, R, C, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
-            else if (rpt <= 8 && G >= 256) qk_pair_step<8>(wp, wq, jp, jq, R, C, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
-            else qk_pair_step_generic(wp, wq, jp, jq, R, C, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
+            if (rpt <= 1) qk_pair_step<1>(wp, wq, R, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
+            else if (rpt <= 2) qk_pair_step<2>(wp, wq, R, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
+            else if (rpt <= 4) qk_pair_step<4>(wp, wq, R, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
+            else if (rpt <= 8 && G != 128) qk_pair_step<8>(wp, wq, R, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
+            else qk_pair_step_generic(wp, wq, R, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
           QK_PAR_END
 #else
           QK_PAR_BEGIN(tid)
@@ -418,7 +408,6 @@ QK_DEV void qk_jacobi(SimCtx& c, int R, int C) {
               const int rot = qk_rotation(a, b, gr, gi, tol2, floor2, abs2, cs, f);
               if (rot) {
                 qk_rotate_rows(W + (size_t)p * ldw, W + (size_t)q * ldw, R, sl, tpp, cs, f);
-                qk_rotate_rows(J + (size_t)p * C, J + (size_t)q * C, C, sl, tpp, cs, f);
                 if (sl == 0 && rot == 2) c.sh->rotated = 1;
               }
             }
@@ -520,16 +509,11 @@ QK_DEV void qk_op_2q(SimCtx& c, const QkOp& op) {
   const int R = transposed ? n2 : m;
   const int C = transposed ? m : n2;
   const int ldw = R;
-  c128* A = qk_site(c, k);
-  c128* B = qk_site(c, k + 1);
-  c128* As = c.J;
-  c128* Bs = c.J + (size_t)ca * 2 * cb;
+  c128* A = qk_site(c, k);       // [a][l][b]   (global, L1/L2 resident; both sites stay intact until the
+  c128* B = qk_site(c, k + 1);   // [b][r][c]    new tensors are complete)
   c128* W = c.W;
-  c128* J = c.J;
 
   QK_PAR_BEGIN(tid)
-    for (int i = tid; i < ca * 2 * cb; i += G) As[i] = A[i];
-    for (int i = tid; i < cb * 2 * cc; i += G) Bs[i] = B[i];
     if (tid == 0) qk_build_gate_2q_fused(op, c.x, c.gate, c.gacc, (c128*)c.scr);
   QK_PAR_END
 
@@ -541,8 +525,8 @@ QK_DEV void qk_op_2q(SimCtx& c, const QkOp& op) {
       for (int l = 0; l < 2; ++l)
         for (int r = 0; r < 2; ++r) {
           c128 acc = cmake(0, 0);
-          const c128* ap = As + (size_t)(a * 2 + l) * cb;
-          const c128* bp = Bs + (size_t)r * cc + cidx;
+          const c128* ap = A + (size_t)(a * 2 + l) * cb;
+          const c128* bp = B + (size_t)r * cc + cidx;
           for (int b = 0; b < cb; ++b) cfma(acc, ap[b], bp[(size_t)b * 2 * cc]);
           t[l * 2 + r] = acc;
         }
@@ -555,13 +539,6 @@ QK_DEV void qk_op_2q(SimCtx& c, const QkOp& op) {
           if (!transposed) W[row + (size_t)col * ldw] = acc;
           else W[col + (size_t)row * ldw] = cconj(acc);
         }
-    }
-  QK_PAR_END
-
-  QK_PAR_BEGIN(tid)
-    for (int i = tid; i < C * C; i += G) {
-      const int col = i / C, row = i - col * C;
-      J[i] = cmake(row == col ? 1.0 : 0.0, 0.0);
     }
   QK_PAR_END
 
@@ -584,35 +561,163 @@ QK_DEV void qk_op_2q(SimCtx& c, const QkOp& op) {
         rk += (u > v) || (u == v && i < j);
       }
       c.order[rk] = j;
-      const double sg = sqrt(v);                       // singular value and its inverse, once per column
-      c.diag[j] = cmake(sg, sg > 0.0 ? 1.0 / sg : 0.0);
     }
   QK_PAR_END
   QK_PAR_BEGIN(tid)
-    if (tid == 0) qk_truncate(c, C, c.P->cap[k + 1]);
+    if (tid == 0) {
+      qk_truncate(c, C, c.P->cap[k + 1]);
+      // Column swaps that bring the kept columns, in sorted order, to the front of W.  pos[j] = where
+      // original column j is now, at[p] = which original column sits at p (int scratch in scr).
+      int* pos = (int*)c.scr;
+      int* at = pos + C;
+      for (int j = 0; j < C; ++j) { pos[j] = j; at[j] = j; }
+      double total = 0.0;
+      for (int j = 0; j < C; ++j) total += c.nrm2[j];
+      const double dead = c.P->floor_rel * total;
+      for (int t = 0; t < c.sh->keep; ++t) {
+        const int j = c.order[t], p = pos[j];
+        c.swp[t] = p;
+        if (p != t) { const int jj = at[t]; at[p] = jj; pos[jj] = p; at[t] = j; pos[j] = t; }
+        // singular value and its inverse.  A kept column below the Jacobi floor was never orthogonalised
+        // against the others, so the projection below is meaningless for it: its inverse is set to 0, which
+        // drops the (<= 1e-14 relative) amplitude it carries.
+        const double v = c.nrm2[j];
+        const double sg = sqrt(v);
+        c.diag[t] = cmake(sg, (sg > 0.0 && (v > dead || t == 0)) ? 1.0 / sg : 0.0);
+      }
+    }
   QK_PAR_END
 
   const int keep = c.sh->keep;
   const double renorm = c.sh->renorm;
   const bool right = (op.dir == QK_DIR_RIGHT);
   QK_PAR_BEGIN(tid)
+    for (int row = tid; row < R; row += G)
+      for (int t = 0; t < keep; ++t) {
+        const int p = c.swp[t];
+        if (p != t) {
+          const c128 x = W[row + (size_t)t * ldw];
+          W[row + (size_t)t * ldw] = W[row + (size_t)p * ldw];
+          W[row + (size_t)p * ldw] = x;
+        }
+      }
+  QK_PAR_END
+
+  // W[:, t] = sigma_t u_t now (t < keep).  The other factor follows from W_out^dag W_in = Sigma^2 V^dag, with
+  // W_in = theta (or theta^dag) contracted in two halves so that theta is never rebuilt:
+  //   plain      : new right site  B'[t,R,c] = s_t sum_{r,b} F[t,R,r,b] B[b,r,c],
+  //                F[t,R,r,b] = sum_{L,l} g[(L,R),(l,r)] sum_a conj(W[(a,L),t]) A[a,l,b]
+  //   transposed : new left site   A'[a,L,t] = s_t sum_{l,b} A[a,l,b] F[t,L,l,b],
+  //                F[t,L,l,b] = sum_{R,r} g[(L,R),(l,r)] sum_c B[b,r,c] W[(R,c),t]
+  // F is produced in tiles of TT values of t (one (t, b) unit per thread) in c.ef; the new tensor is staged in
+  // the tail of W (keep * (R + C) <= rmax^2) because both old sites are still being read.
+  c128* S = W + (size_t)R * keep;
+  int TT = G / cb;
+  if (TT < 1) TT = 1;
+  const int upt = (TT * cb + G - 1) / G;   // units per thread (1 unless cb > G)
+  (void)upt;
+  for (int t0 = 0; t0 < keep; t0 += TT) {
+    QK_PAR_BEGIN(tid)
+      for (int u = tid; u < TT * cb; u += G) {
+        const int tt = u / cb, b = u - tt * cb;
+        const int t = t0 + tt;
+        if (t < keep) {
+          const c128* w = W + (size_t)t * ldw;
+          c128 e[4];
+          e[0] = e[1] = e[2] = e[3] = cmake(0, 0);
+          if (!transposed) {
+            for (int a = 0; a < ca; ++a) {
+              const c128 w0 = w[a * 2], w1 = w[a * 2 + 1];
+              const c128 a0 = A[(size_t)(a * 2) * cb + b], a1 = A[(size_t)(a * 2 + 1) * cb + b];
+              cfmac(e[0], w0, a0); cfmac(e[1], w0, a1);     // e[L*2+l] += conj(W[(a,L),t]) A[a,l,b]
+              cfmac(e[2], w1, a0); cfmac(e[3], w1, a1);
+            }
+          } else {
+            const c128* b0 = B + (size_t)(b * 2) * cc;
+            const c128* b1 = b0 + cc;
+            for (int cidx = 0; cidx < cc; ++cidx) {
+              const c128 w0 = w[cidx], w1 = w[cc + cidx];
+              const c128 v0 = b0[cidx], v1 = b1[cidx];
+              cfma(e[0], v0, w0); cfma(e[1], v1, w0);       // e[R*2+r] += B[b,r,c] W[(R,c),t]
+              cfma(e[2], v0, w1); cfma(e[3], v1, w1);
+            }
+          }
+          c128* f = c.ef + (size_t)u * 4;
+          if (!transposed) {
+            for (int Rr = 0; Rr < 2; ++Rr)
+              for (int r = 0; r < 2; ++r) {
+                c128 acc = cmake(0, 0);
+                for (int L = 0; L < 2; ++L)
+                  for (int l = 0; l < 2; ++l) cfma(acc, c.gate[(L * 2 + Rr) * 4 + (l * 2 + r)], e[L * 2 + l]);
+                f[Rr * 2 + r] = acc;
+              }
+          } else {
+            for (int L = 0; L < 2; ++L)
+              for (int l = 0; l < 2; ++l) {
+                c128 acc = cmake(0, 0);
+                for (int Rr = 0; Rr < 2; ++Rr)
+                  for (int r = 0; r < 2; ++r) cfma(acc, c.gate[(L * 2 + Rr) * 4 + (l * 2 + r)], e[Rr * 2 + r]);
+                f[L * 2 + l] = acc;
+              }
+          }
+        }
+      }
+    QK_PAR_END
+    QK_PAR_BEGIN(tid)
+      if (!transposed) {
+        for (int idx = tid; idx < TT * n2; idx += G) {
+          const int tt = idx / n2, col = idx - tt * n2;
+          const int t = t0 + tt;
+          if (t < keep) {
+            const int Rr = col / cc, cidx = col - Rr * cc;
+            const c128* f = c.ef + (size_t)tt * cb * 4 + Rr * 2;
+            c128 acc = cmake(0, 0);
+            for (int b = 0; b < cb; ++b) {
+              cfma(acc, f[(size_t)b * 4], B[(size_t)(b * 2) * cc + cidx]);
+              cfma(acc, f[(size_t)b * 4 + 1], B[(size_t)(b * 2 + 1) * cc + cidx]);
+            }
+            const double sg = c.diag[t].x, isg = c.diag[t].y;
+            (void)sg;
+            S[(size_t)t * n2 + col] = cscale(acc, right ? renorm * isg : isg * isg);
+          }
+        }
+      } else {
+        for (int idx = tid; idx < TT * m; idx += G) {
+          const int tt = idx / m, row = idx - tt * m;
+          const int t = t0 + tt;
+          if (t < keep) {
+            const int a = row >> 1, L = row & 1;
+            const c128* f = c.ef + (size_t)tt * cb * 4 + L * 2;
+            c128 acc = cmake(0, 0);
+            for (int b = 0; b < cb; ++b) {
+              cfma(acc, A[(size_t)(a * 2) * cb + b], f[(size_t)b * 4]);
+              cfma(acc, A[(size_t)(a * 2 + 1) * cb + b], f[(size_t)b * 4 + 1]);
+            }
+            const double isg = c.diag[t].y;
+            S[(size_t)row * keep + t] = cscale(acc, right ? isg * isg : renorm * isg);
+          }
+        }
+      }
+    QK_PAR_END
+  }
+
+  QK_PAR_BEGIN(tid)
     // left site  [a][L][t]  (m x keep),  right site [t][R][c]  (keep x n2)
     for (int idx = tid; idx < m * keep; idx += G) {
       const int row = idx / keep, t = idx - row * keep;
-      const int j = c.order[t];
-      const double sg = c.diag[j].x, isg = c.diag[j].y;
+      const double sg = c.diag[t].x, isg = c.diag[t].y;
       c128 v;
-      if (!transposed) v = cscale(W[row + (size_t)j * ldw], right ? isg : renorm);        // W = U S
-      else v = cscale(J[row + (size_t)j * C], right ? 1.0 : sg * renorm);                // U = J
+      if (!transposed) v = cscale(W[row + (size_t)t * ldw], right ? isg : renorm);        // W = U S
+      else v = S[idx];
+      (void)sg;
       A[idx] = v;
     }
     for (int idx = tid; idx < keep * n2; idx += G) {
       const int t = idx / n2, col = idx - t * n2;
-      const int j = c.order[t];
-      const double sg = c.diag[j].x, isg = c.diag[j].y;
+      const double isg = c.diag[t].y;
       c128 v;
-      if (!transposed) v = cscale(cconj(J[col + (size_t)j * C]), right ? sg * renorm : 1.0);   // V^dag = J^dag
-      else v = cscale(cconj(W[col + (size_t)j * ldw]), right ? renorm : isg);                  // S V^dag = W^dag
+      if (!transposed) v = S[idx];
+      else v = cscale(cconj(W[col + (size_t)t * ldw]), right ? renorm : isg);            // S V^dag = W^dag
       B[idx] = v;
     }
     if (tid == 0) c.chi[k + 1] = keep;
@@ -753,18 +858,21 @@ QK_DEV void qk_op_move(SimCtx& c, const QkOp& op) {
       }
     }
   QK_PAR_END
-  c128* Qm = c.J;
+  // W holds R x C <= rmax^2 / 2 entries; Q (R x kk) goes to the other half, which then stages the neighbour
+  c128* Qm = c.W + ((size_t)c.P->rmax * c.P->rmax) / 2;
   const int kk = qk_householder_qr<G>(c, R, C, Qm);
-  c128* Nb = c.J + (size_t)R * kk;   // staging for the neighbour site
+  c128* Nb = Qm;
   if (to_right) {
     const int cr2 = c.chi[s + 2];
     c128* Bn = qk_site(c, s + 1);
     QK_PAR_BEGIN(tid)
-      for (int i = tid; i < C * 2 * cr2; i += G) Nb[i] = Bn[i];
       for (int i = tid; i < R * kk; i += G) {          // A[(a,p), t] = Q[(a,p), t]
         const int row = i / kk, t = i - row * kk;
         A[i] = Qm[row + (size_t)t * R];
       }
+    QK_PAR_END
+    QK_PAR_BEGIN(tid)
+      for (int i = tid; i < C * 2 * cr2; i += G) Nb[i] = Bn[i];
     QK_PAR_END
     QK_PAR_BEGIN(tid)
       for (int i = tid; i < kk * 2 * cr2; i += G) {    // B'[t, (p,c)] = sum_b R[t,b] B[b,(p,c)]
@@ -779,11 +887,13 @@ QK_DEV void qk_op_move(SimCtx& c, const QkOp& op) {
     const int cl0 = c.chi[s - 1];
     c128* An = qk_site(c, s - 1);
     QK_PAR_BEGIN(tid)
-      for (int i = tid; i < cl0 * 2 * C; i += G) Nb[i] = An[i];
       for (int i = tid; i < kk * R; i += G) {          // A[t,(p,b)] = conj(Q[(p,b), t])
         const int t = i / R, pb = i - t * R;
         A[i] = cconj(Qm[pb + (size_t)t * R]);
       }
+    QK_PAR_END
+    QK_PAR_BEGIN(tid)
+      for (int i = tid; i < cl0 * 2 * C; i += G) Nb[i] = An[i];
     QK_PAR_END
     QK_PAR_BEGIN(tid)
       for (int i = tid; i < cl0 * 2 * kk; i += G) {    // A'[(a',p'), t] = sum_a A[(a',p'), a] conj(R[t,a])
