@@ -238,17 +238,7 @@ int qk_simulate_dev(const qk_plan* plan, int device, void* stream_v, const doubl
   QK_TRY(cudaEventCreate(&e0), "cudaEventCreate");
   QK_TRY(cudaEventCreate(&e1), "cudaEventCreate");
   QK_TRY(cudaEventRecord(e0, stream), "cudaEventRecord");
-  // Threads per datapoint.  At bond cap 16 a 128-thread group has the lower single-datapoint latency, a 64-thread
-  // group the lower cost per co-resident datapoint (measured: 9.2 + 1.14 c ms vs 11.6 + 0.1 c ms with c
-  // datapoints resident per SM), so large batches take 64.
-  int G = plan->threads;
-  size_t smem = plan->smem_bytes;
-  if (!getenv("QK_SIM_THREADS") && G == 128) {
-    int sms = 0;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    if (sms > 0 && N > 2 * sms) { G = 64; smem = qk_sim_smem_bytes(plan->n, plan->rmax, G); }
-  }
-  QK_TRY(qk_launch_sim(P, G, smem, counter, stream, &b->sim_grid), "stage-1 kernel launch");
+  QK_TRY(qk_launch_sim(P, plan->threads, plan->smem_bytes, counter, stream, &b->sim_grid), "stage-1 kernel launch");
   QK_TRY(cudaEventRecord(e1, stream), "cudaEventRecord");
   QK_TRY(cudaEventSynchronize(e1), "stage-1 kernel");
   cudaEventElapsedTime(&b->sim_ms, e0, e1);

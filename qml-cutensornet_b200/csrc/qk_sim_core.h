@@ -49,6 +49,7 @@ struct SimShared {
   int sweeps;
   int max_chi;
   double renorm;
+  double total;     // Frobenius norm^2 of the matrix the last Jacobi ran on
   double fidelity;
   double trunc_weight;
   double f0;
@@ -350,6 +351,9 @@ QK_DEV void qk_jacobi(SimCtx& c, int R, int C) {
   double total = 0.0;
   for (int t = 0; t < G; ++t) total += c.scr[t];
   QK_BARRIER();
+  QK_PAR_BEGIN(tid)
+    if (tid == 0) c.sh->total = total;
+  QK_PAR_END
   const double floor2 = c.P->floor_rel * total;
   // inner products below abs_rel * total are rounding-level relative to the dominant columns: rotating
   // them only polishes directions whose weight is far below any truncation threshold
@@ -553,6 +557,9 @@ QK_DEV void qk_op_2q(SimCtx& c, const QkOp& op) {
     }
   QK_PAR_END
   QK_PAR_BEGIN(tid)
+    const double dead = c.P->floor_rel * c.sh->total;
+    int* pos = (int*)c.scr;     // int scratch for the swap list below
+    int* at = pos + C;
     for (int j = tid; j < C; j += G) {
       const double v = c.nrm2[j];
       int rk = 0;
@@ -561,29 +568,29 @@ QK_DEV void qk_op_2q(SimCtx& c, const QkOp& op) {
         rk += (u > v) || (u == v && i < j);
       }
       c.order[rk] = j;
+      // singular value and its inverse, indexed by sorted position.  A column below the Jacobi floor was never
+      // orthogonalised against the others, so the projection below is meaningless for it: its inverse is
+      // set to 0, which drops the (<= 1e-14 relative) amplitude it carries if the truncation rule keeps it.
+      const double sg = sqrt(v);
+      c.diag[rk] = cmake(sg, (sg > 0.0 && (v > dead || rk == 0)) ? 1.0 / sg : 0.0);
+      pos[j] = j; at[j] = j;
     }
   QK_PAR_END
   QK_PAR_BEGIN(tid)
     if (tid == 0) {
       qk_truncate(c, C, c.P->cap[k + 1]);
-      // Column swaps that bring the kept columns, in sorted order, to the front of W.  pos[j] = where
-      // original column j is now, at[p] = which original column sits at p (int scratch in scr).
-      int* pos = (int*)c.scr;
-      int* at = pos + C;
-      for (int j = 0; j < C; ++j) { pos[j] = j; at[j] = j; }
-      double total = 0.0;
-      for (int j = 0; j < C; ++j) total += c.nrm2[j];
-      const double dead = c.P->floor_rel * total;
-      for (int t = 0; t < c.sh->keep; ++t) {
-        const int j = c.order[t], p = pos[j];
-        c.swp[t] = p;
-        if (p != t) { const int jj = at[t]; at[p] = jj; pos[jj] = p; at[t] = j; pos[j] = t; }
-        // singular value and its inverse.  A kept column below the Jacobi floor was never orthogonalised
-        // against the others, so the projection below is meaningless for it: its inverse is set to 0, which
-        // drops the (<= 1e-14 relative) amplitude it carries.
-        const double v = c.nrm2[j];
-        const double sg = sqrt(v);
-        c.diag[t] = cmake(sg, (sg > 0.0 && (v > dead || t == 0)) ? 1.0 / sg : 0.0);
+      // The new tensor is staged behind W.  If W (R x C) plus the staging area (keep x C) exceed the
+      // region, the kept columns are first compacted to the front of W by column swaps (sorted order);
+      // otherwise they are addressed through order[].  pos[j] = where original column j is now,
+      // at[p] = which original column sits at p.
+      if ((size_t)R * C + (size_t)c.sh->keep * C > (size_t)c.P->rmax * c.P->rmax) {
+        int* pos = (int*)c.scr;
+        int* at = pos + C;
+        for (int t = 0; t < c.sh->keep; ++t) {
+          const int j = c.order[t], p = pos[j];
+          c.swp[t] = p;
+          if (p != t) { const int jj = at[t]; at[p] = jj; pos[jj] = p; at[t] = j; pos[j] = t; }
+        }
       }
     }
   QK_PAR_END
@@ -591,19 +598,23 @@ QK_DEV void qk_op_2q(SimCtx& c, const QkOp& op) {
   const int keep = c.sh->keep;
   const double renorm = c.sh->renorm;
   const bool right = (op.dir == QK_DIR_RIGHT);
-  QK_PAR_BEGIN(tid)
-    for (int row = tid; row < R; row += G)
-      for (int t = 0; t < keep; ++t) {
-        const int p = c.swp[t];
-        if (p != t) {
-          const c128 x = W[row + (size_t)t * ldw];
-          W[row + (size_t)t * ldw] = W[row + (size_t)p * ldw];
-          W[row + (size_t)p * ldw] = x;
+  const bool compact = (size_t)R * C + (size_t)keep * C > (size_t)c.P->rmax * c.P->rmax;
+  if (compact) {
+    QK_PAR_BEGIN(tid)
+      for (int row = tid; row < R; row += G)
+        for (int t = 0; t < keep; ++t) {
+          const int p = c.swp[t];
+          if (p != t) {
+            const c128 x = W[row + (size_t)t * ldw];
+            W[row + (size_t)t * ldw] = W[row + (size_t)p * ldw];
+            W[row + (size_t)p * ldw] = x;
+          }
         }
-      }
-  QK_PAR_END
+    QK_PAR_END
+  }
 
-  // W[:, t] = sigma_t u_t now (t < keep).  The other factor follows from W_out^dag W_in = Sigma^2 V^dag, with
+  // W[:, col(t)] = sigma_t u_t (t < keep), col(t) = t after compaction, order[t] otherwise.
+  // The other factor follows from W_out^dag W_in = Sigma^2 V^dag, with
   // W_in = theta (or theta^dag) contracted in two halves so that theta is never rebuilt:
   //   plain      : new right site  B'[t,R,c] = s_t sum_{r,b} F[t,R,r,b] B[b,r,c],
   //                F[t,R,r,b] = sum_{L,l} g[(L,R),(l,r)] sum_a conj(W[(a,L),t]) A[a,l,b]
@@ -611,7 +622,7 @@ QK_DEV void qk_op_2q(SimCtx& c, const QkOp& op) {
   //                F[t,L,l,b] = sum_{R,r} g[(L,R),(l,r)] sum_c B[b,r,c] W[(R,c),t]
   // F is produced in tiles of TT values of t (one (t, b) unit per thread) in c.ef; the new tensor is staged in
   // the tail of W (keep * (R + C) <= rmax^2) because both old sites are still being read.
-  c128* S = W + (size_t)R * keep;
+  c128* S = W + (size_t)R * (compact ? keep : C);
   int TT = G / cb;
   if (TT < 1) TT = 1;
   const int upt = (TT * cb + G - 1) / G;   // units per thread (1 unless cb > G)
@@ -622,7 +633,7 @@ QK_DEV void qk_op_2q(SimCtx& c, const QkOp& op) {
         const int tt = u / cb, b = u - tt * cb;
         const int t = t0 + tt;
         if (t < keep) {
-          const c128* w = W + (size_t)t * ldw;
+          const c128* w = W + (size_t)(compact ? t : c.order[t]) * ldw;
           c128 e[4];
           e[0] = e[1] = e[2] = e[3] = cmake(0, 0);
           if (!transposed) {
@@ -707,7 +718,7 @@ QK_DEV void qk_op_2q(SimCtx& c, const QkOp& op) {
       const int row = idx / keep, t = idx - row * keep;
       const double sg = c.diag[t].x, isg = c.diag[t].y;
       c128 v;
-      if (!transposed) v = cscale(W[row + (size_t)t * ldw], right ? isg : renorm);        // W = U S
+      if (!transposed) v = cscale(W[row + (size_t)(compact ? t : c.order[t]) * ldw], right ? isg : renorm);   // W = U S
       else v = S[idx];
       (void)sg;
       A[idx] = v;
@@ -717,7 +728,7 @@ QK_DEV void qk_op_2q(SimCtx& c, const QkOp& op) {
       const double isg = c.diag[t].y;
       c128 v;
       if (!transposed) v = S[idx];
-      else v = cscale(cconj(W[col + (size_t)t * ldw]), right ? renorm : isg);            // S V^dag = W^dag
+      else v = cscale(cconj(W[col + (size_t)(compact ? t : c.order[t]) * ldw]), right ? renorm : isg);   // S V^dag = W^dag
       B[idx] = v;
     }
     if (tid == 0) c.chi[k + 1] = keep;
