@@ -62,10 +62,11 @@ def build_kernel_matrix(mpi_comm, ansatz, X, Y=None, info_file="info_file", trun
     for name, _, _ in gates:
         if name not in _KNOWN:
             raise RuntimeError(f"Unrecognised {name}.")
-    plans = {}
+    # compiled schedules are kept on the ansatz: the train and the test kernel of one run share them
+    plans = ansatz.__dict__.setdefault("_qk_plans", {})
 
     def plan_factory(cap, early_exit=False):
-        key = (cap, bool(early_exit))
+        key = (QK_TRUNC_ITENSORS, float(truncation_error), cap, bool(early_exit), os.environ.get("QK_SCHEDULE", ""))
         if key not in plans:
             plans[key] = Plan(n_qubits, gates, QK_TRUNC_ITENSORS, float(truncation_error), cap,
                               QK_PLAN_EARLY_EXIT if early_exit else 0)

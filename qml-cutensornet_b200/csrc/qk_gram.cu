@@ -292,7 +292,7 @@ __device__ __forceinline__ void qk_site_dispatch(double (&Er)[NT][NT][2], double
 template <int NT> struct GramCfg { static constexpr int PPW = 1; static constexpr int TI = QK_TI * PPW; };
 
 template <int NT>
-__global__ void __launch_bounds__(QK_GRAM_WARPS * 32, NT == 1 ? 4 : 1) qk_gram_dmma_kernel(const __grid_constant__ GramParams P) {
+__global__ void __launch_bounds__(QK_GRAM_WARPS * 32, NT == 1 ? 4 : (QK_GRAM_WARPS <= 4 ? 2 : 1)) qk_gram_dmma_kernel(const __grid_constant__ GramParams P) {
   constexpr int PPW = GramCfg<NT>::PPW;
   constexpr int TI = GramCfg<NT>::TI;
   extern __shared__ __align__(128) unsigned char gsm[];
