@@ -14,7 +14,7 @@ from __future__ import annotations
 import json
 import os
 import sys
-from statistics import mean
+
 
 import numpy as np
 
@@ -87,7 +87,13 @@ def build_kernel_matrix(mpi_comm, ansatz, X, Y=None, info_file=None, truncation_
                               QK_PLAN_EARLY_EXIT if early_exit else 0)
         return plans[key]
 
-    cap0 = int(chi) if chi is not None else _initial_cap(ansatz, truncation_error)
+    if chi is not None:
+        cap0 = int(chi)
+    else:
+        caps = ansatz.__dict__.setdefault("_qk_cap0", {})
+        if float(truncation_error) not in caps:
+            caps[float(truncation_error)] = _initial_cap(ansatz, truncation_error)
+        cap0 = caps[float(truncation_error)]
     plan_factory(cap0)
     if rank == root:
         duration = Wtime() - start_time
@@ -109,20 +115,20 @@ def build_kernel_matrix(mpi_comm, ansatz, X, Y=None, info_file=None, truncation_
             per_circ += [prof["sim_ms_y"] * 1e-3 / n_y] * n_y
         med, q1, q3 = _percentiles(per_circ)
         profiling_dict["r0_circ_sim"] = [sim_s, "seconds"]
-        profiling_dict["avg_circ_sim"] = [mean(per_circ), "seconds"]
+        profiling_dict["avg_circ_sim"] = [float(np.mean(per_circ)), "seconds"]
         profiling_dict["median_circ_sim"] = [med, "seconds"]
         profiling_dict["q1_circ_sim"] = [q1, "seconds"]
         profiling_dict["q3_circ_sim"] = [q3, "seconds"]
         nbytes = list(ix["nbytes"]) + (list(iy["nbytes"]) if iy is not None else list(ix["nbytes"]))
         fids = list(ix["fidelity"]) + (list(iy["fidelity"]) if iy is not None else list(ix["fidelity"]))
-        total_mem = float(sum(nbytes)) / (1024 ** 2)
+        total_mem = float(np.sum(nbytes)) / (1024 ** 2)
         profiling_dict["gpu_mps_mem"] = [total_mem, "MiB"]
         profiling_dict["avg_mps_mem"] = [total_mem / max(len(nbytes), 1), "MiB"]
-        profiling_dict["avg_fidelity"] = [float(sum(fids)) / max(len(fids), 1), ""]
-        chi_x = [int(c.max()) for c in ix["chi"]] or [1]
-        chi_y = [int(c.max()) for c in iy["chi"]] if iy is not None else chi_x
-        profiling_dict["ave max chi x"] = (mean(chi_x), "chi x")
-        profiling_dict["ave max chi y"] = (mean(chi_y or [1]), "chi y")
+        profiling_dict["avg_fidelity"] = [float(np.sum(fids)) / max(len(fids), 1), ""]
+        chi_x = np.asarray(ix["chi"]).max(axis=1) if len(ix["chi"]) else np.ones(1)
+        chi_y = (np.asarray(iy["chi"]).max(axis=1) if len(iy["chi"]) else np.ones(1)) if iy is not None else chi_x
+        profiling_dict["ave max chi x"] = (float(np.mean(chi_x)), "chi x")
+        profiling_dict["ave max chi y"] = (float(np.mean(chi_y)), "chi y")
         profiling_dict["r_nonRR_recv"] = [0, "seconds"]
         profiling_dict["r0_RR_recv"] = [prof["exchange_s"], "seconds"]
         n_pairs = len(X) * (len(X) + 1) // 2 if Y is None else len(X) * len(Y)

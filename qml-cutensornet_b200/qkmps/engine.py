@@ -133,8 +133,7 @@ def _simulate_shard(plan_factory, X_shard, device, chi_cap, comm, n_qubits, esca
     if isinstance(X_shard, torch.Tensor):
         xt = X_shard.contiguous()
     elif len(X_shard):
-        xt = torch.from_numpy(np.ascontiguousarray(X_shard, dtype=np.float64)).pin_memory().to(
-            f"cuda:{device}", non_blocking=True)
+        xt = torch.from_numpy(np.ascontiguousarray(X_shard, dtype=np.float64)).to(f"cuda:{device}")
     else:
         xt = torch.empty((0, n_qubits), device=f"cuda:{device}", dtype=torch.float64)
     torch.cuda.current_stream().synchronize()
