@@ -122,10 +122,10 @@ __device__ __forceinline__ void qk_mbar_wait(uint32_t bar, uint32_t parity) {
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"   // %3: suspend-time hint (ns)
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(100000u)
         : "memory");
   } while (!ok);
 }
@@ -209,9 +209,10 @@ __device__ __forceinline__ void qk_site_step(double (&Er)[NT][NT][2], double (&E
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const double u1 = T1[p][a][b][e], u2 = T2[p][a][b][e], u3 = T3[p][a][b][e];
-          T1[p][a][b][e] = u1 - u2;
-          T2[p][a][b][e] = u3 - u1 - u2;
-          T3[p][a][b][e] = u3 - 2.0 * u2;
+          const double tr = u1 - u2, ts = fma(-2.0, u2, u3);
+          T1[p][a][b][e] = tr;
+          T2[p][a][b][e] = ts - tr;
+          T3[p][a][b][e] = ts;
         }
   // step 2: E'[b'][c'] += sum_{a,p} conj(A_y[a,p,b']) * T_p[a][c']:  S1 = Ar Tr, S2 = Ai Ti, S3 = (Ar-Ai)(Tr+Ti)
   double F1[MY][MX][2], F2[MY][MX][2], F3[MY][MX][2];
@@ -254,9 +255,10 @@ __device__ __forceinline__ void qk_site_step(double (&Er)[NT][NT][2], double (&E
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const double u1 = F1[a][b][e], u2 = F2[a][b][e], u3 = F3[a][b][e];
-        Er[a][b][e] = u1 + u2;
-        Ei[a][b][e] = u3 - u1 + u2;
-        Es[a][b][e] = u3 + 2.0 * u2;
+        const double er = u1 + u2, es = fma(2.0, u2, u3);
+        Er[a][b][e] = er;
+        Ei[a][b][e] = es - er;
+        Es[a][b][e] = es;
       }
 }
 
