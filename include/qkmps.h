@@ -150,6 +150,16 @@ int qk_gram_frags(int device, void* stream, int n_qubits,
                   const int32_t* Dy, const void* fragY, int Ny,
                   const int32_t* tiles /*[n_tiles][4] = r0,r1,c0,c1*/, int n_tiles, int symmetric,
                   double* K_dev, int64_t ldk, float* ms_out);
+/* Same Gram tiles for batches whose bond dimensions are all <= 4 (max_chi; the regime of the reference's published
+ * scaling runs, runs/runtime_scaling: chi = 2): one lane per (y, x) pair on the FP64 CUDA cores, reading the
+ * unpadded stage-1 stores [N][state_stride] c128 + chi [N][n+1] of states simulated with `plan` (raw device
+ * pointers so that shards gathered from other ranks can be passed).  symmetric != 0: storeY / chiY ignored. */
+int qk_batch_store(const qk_batch* batch, void** store_dev, int64_t* state_stride_c128, void** chi_dev);
+int qk_gram_lane(const qk_plan* plan, int device, void* stream, int max_chi,
+                 const void* storeX, const int32_t* chiX, int Nx,
+                 const void* storeY, const int32_t* chiY, int Ny,
+                 const int32_t* tiles /*[n_tiles][4] = r0,r1,c0,c1*/, int n_tiles, int symmetric,
+                 double* K_dev, int64_t ldk, float* ms_out);
 /* CUDA-core FP64 cross-check kernel working on the unpadded stores (any chi <= cap) */
 int qk_gram_store(const qk_batch* X, const qk_batch* Y_or_null, double* K_host, int64_t ldk, float* ms_out);
 

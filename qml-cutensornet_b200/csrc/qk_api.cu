@@ -600,6 +600,73 @@ int qk_gram_store(const qk_batch* X, const qk_batch* Y, double* K_host, int64_t 
   return QK_OK;
 }
 
+// ---------------------------------------------------------------- low-chi stage 2 on the stores
+int qk_batch_store(const qk_batch* b, void** store_dev, int64_t* state_stride, void** chi_dev) {
+  if (!b) return fail(QK_ERR_ARG, "NULL batch");
+  if (store_dev) *store_dev = b->store;
+  if (state_stride) *state_stride = b->state_stride;
+  if (chi_dev) *chi_dev = b->chi;
+  return QK_OK;
+}
+
+int qk_gram_lane(const qk_plan* plan, int device, void* stream_v, int max_chi, const void* storeX, const int32_t* chiX,
+                 int Nx, const void* storeY, const int32_t* chiY, int Ny, const int32_t* tiles, int n_tiles,
+                 int symmetric, double* K_dev, int64_t ldk, float* ms_out) {
+  if (!plan || !storeX || !chiX || Nx < 1 || !K_dev || n_tiles < 0 || (n_tiles > 0 && !tiles))
+    return fail(QK_ERR_ARG, "bad arguments");
+  if (symmetric) { storeY = storeX; chiY = chiX; Ny = Nx; }
+  if (!storeY || !chiY || Ny < 1) return fail(QK_ERR_ARG, "bad Y arguments");
+  if (ldk < Nx) return fail(QK_ERR_ARG, "ldk must be >= Nx");
+  if (max_chi < 1 || max_chi > 4) return fail(QK_ERR_LIMIT, "the lane-per-pair overlap kernel supports bond dimensions <= 4");
+  QK_CUDA(cudaSetDevice(device), "cudaSetDevice");
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  int TX = 0, TY = 0;
+  qk_gram_lane_tile_shape(&TX, &TY);
+  std::vector<int4> cta;
+  for (int t = 0; t < n_tiles; ++t) {
+    const int r0 = tiles[4 * t], r1 = tiles[4 * t + 1], c0 = tiles[4 * t + 2], c1 = tiles[4 * t + 3];
+    if (r0 < 0 || c0 < 0 || r1 > Ny || c1 > Nx || r0 > r1 || c0 > c1) return fail(QK_ERR_ARG, "tile out of range");
+    for (int y0 = r0; y0 < r1; y0 += TY)
+      for (int x0 = c0; x0 < c1; x0 += TX) {
+        const int ye = std::min(y0 + TY, r1), xe = std::min(x0 + TX, c1);
+        if (symmetric && x0 > ye - 1) continue;
+        cta.push_back(make_int4(y0, x0, ye, xe));
+      }
+  }
+  if (cta.empty()) { if (ms_out) *ms_out = 0.f; return QK_OK; }
+  const size_t nb = (size_t)(plan->n + 1);
+  const size_t o_off = (nb * sizeof(int32_t) + 15) & ~(size_t)15, t_off = (o_off + nb * sizeof(int64_t) + 15) & ~(size_t)15;
+  std::vector<unsigned char> hbuf(t_off + cta.size() * sizeof(int4));
+  memcpy(hbuf.data(), plan->cap.data(), nb * sizeof(int32_t));
+  memcpy(hbuf.data() + o_off, plan->site_off.data(), nb * sizeof(int64_t));
+  memcpy(hbuf.data() + t_off, cta.data(), cta.size() * sizeof(int4));
+  unsigned char* dbuf = nullptr;
+  QK_CUDA(pool_alloc_t(&dbuf, hbuf.size()), "cudaMalloc(gram scratch)");
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaError_t e = cudaMemcpyAsync(dbuf, hbuf.data(), hbuf.size(), cudaMemcpyHostToDevice, stream);
+  LaneParams P;
+  P.n = plan->n;
+  P.cap = (const int32_t*)dbuf; P.site_off = (const int64_t*)(dbuf + o_off); P.state_stride = plan->state_stride;
+  P.storeX = (const c128*)storeX; P.chiX = chiX; P.storeY = (const c128*)storeY; P.chiY = chiY;
+  P.Nx = Nx; P.Ny = Ny;
+  P.tiles = (const int4*)(dbuf + t_off); P.n_cta_tiles = (int)cta.size();
+  P.symmetric = symmetric ? 1 : 0; P.K = K_dev; P.ldk = ldk;
+  if (e == cudaSuccess) e = cudaEventCreate(&e0);
+  if (e == cudaSuccess) e = cudaEventCreate(&e1);
+  if (e == cudaSuccess) e = cudaEventRecord(e0, stream);
+  if (e == cudaSuccess) e = qk_launch_gram_lane(P, max_chi, stream);
+  if (e == cudaSuccess) e = cudaEventRecord(e1, stream);
+  if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+  float ms = 0.f;
+  if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  pool_free(dbuf);
+  if (e != cudaSuccess) return cuda_fail(e, "lane-per-pair Gram kernel");
+  if (ms_out) *ms_out = ms;
+  return QK_OK;
+}
+
 // ---------------------------------------------------------------- whole path, host buffers
 int qk_gram_host(const qk_plan* plan, int device, const double* X_host, int Nx, const double* Y_host, int Ny, int ldx,
                  double* K_host, int64_t ldk) {

@@ -9,8 +9,8 @@
 // using mma.sync.m8n8k4.f64 (DMMA).  The accumulator layout of one MMA is exactly the B-operand
 // layout of the next when the contraction index is taken in the order (even columns, odd columns),
 // so the site tensors are stored in HBM already permuted into A-fragment order ("frag" layout,
-// written by qk_pack_kernel) and arrive in shared memory through a 3-stage cp.async.bulk (TMA)
-// + mbarrier pipeline issued by one elected lane NS-1 sites ahead of the compute.
+// written by qk_pack_kernel) and arrive in shared memory through an NS-stage (4) cp.async.bulk (TMA)
+// + mbarrier pipeline; the warp that is last to finish a site refills its stage with site s + NS.
 //   * every bond index is stored permuted inside its group of 8 (logical 8t+4e+j <-> physical
 //     8t+2j+e) so that the even / odd k-blocks of a tile hold logical indices 8t..8t+3 / 8t+4..8t+7:
 //     a state whose bond dimension is <= 8t+4 skips the odd k-block (contraction granularity 4).
@@ -29,7 +29,7 @@
 #define QK_TJ 2
 #endif
 #ifndef QK_NS
-#define QK_NS 3
+#define QK_NS 4
 #endif
 #define QK_GRAM_WARPS (QK_TI * QK_TJ)
 
@@ -477,6 +477,153 @@ cudaError_t qk_launch_gram_dmma(const GramParams& P, int maxD, cudaStream_t stre
   if (P.n_cta_tiles <= 0) return cudaSuccess;
   if (maxD <= 8) return launch_gram_nt<1>(P, stream);
   if (maxD <= 16) return launch_gram_nt<2>(P, stream);
+  return cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Lane-per-pair overlap kernel for bond dimensions <= DM (2 or 4).
+// CTA = 16 kets x 8 bras = 128 threads; thread (tx, ty) owns the pair and keeps its transfer matrix E (DM x DM
+// complex) in registers for the whole sweep.  Per site the live prefix of the 24 site tensors involved
+// (<= DM*2*DM c128 each, straight from the stage-1 store) is double-buffered into shared memory with 16-byte
+// cp.async; blocks are skewed by 16 B so that the 16 kets of a warp hit different banks.
+//   t[a]      = sum_c  E[a][c] A_x[c][p][c']                 (for each p, c')
+//   E'[b'][c'] += sum_a conj(A_y[a][p][b']) t[a]
+// 8 DM^3 complex MACs per pair and site, all on the FP64 FMA pipe: 64 lanes/clk/SM.
+// ------------------------------------------------------------------------------------------------
+#define QK_LTX 16
+#define QK_LTY 8
+void qk_gram_lane_tile_shape(int* tx, int* ty) { *tx = QK_LTX; *ty = QK_LTY; }
+
+template <int DM>
+__global__ void __launch_bounds__(QK_LTX * QK_LTY, 3) qk_gram_lane_kernel(const __grid_constant__ LaneParams P) {
+  constexpr int NT = QK_LTX + QK_LTY;
+  constexpr int BLK = DM * 2 * DM + 1;               // c128 per staged block (+1: bank skew)
+  extern __shared__ __align__(16) unsigned char lsm[];
+  const int n = P.n;
+  c128* stage = (c128*)lsm;                           // [2][NT][BLK]
+  int* s_len = (int*)(stage + 2 * NT * BLK);          // [n]   c128 copied per state at site s
+  int64_t* s_off = (int64_t*)(s_len + n + (n & 1));   // [n]
+  unsigned char* s_chi = (unsigned char*)(s_off + n); // [NT][n+1]
+  const int tid = threadIdx.x;
+  const int tx = tid % QK_LTX, ty = tid / QK_LTX;
+  const int4 tile = P.tiles[blockIdx.x];
+  const int y0 = tile.x, x0 = tile.y, y_end = tile.z, x_end = tile.w;
+  const int x = x0 + tx, y = y0 + ty;
+  const bool active = (x < x_end) && (y < y_end) && (!P.symmetric || x <= y);
+
+  for (int s = tid; s < n; s += blockDim.x) {
+    const int full = P.cap[s] * 2 * P.cap[s + 1];
+    s_len[s] = full < DM * 2 * DM ? full : DM * 2 * DM;
+    s_off[s] = P.site_off[s];
+  }
+  for (int i = tid; i < NT * (n + 1); i += blockDim.x) {
+    const int t = i / (n + 1), b = i - t * (n + 1);
+    int idx;
+    const int32_t* chi;
+    if (t < QK_LTX) { idx = x0 + t; if (idx >= P.Nx) idx = P.Nx - 1; chi = P.chiX; }
+    else { idx = y0 + (t - QK_LTX); if (idx >= P.Ny) idx = P.Ny - 1; chi = P.chiY; }
+    s_chi[i] = (unsigned char)chi[(size_t)idx * (n + 1) + b];
+  }
+  __syncthreads();
+
+  auto issue = [&](int s, int buf) {
+    const int len = s_len[s];
+    const int64_t off = s_off[s];
+    for (int i = tid; i < NT * len; i += blockDim.x) {
+      const int t = i / len, ch = i - t * len;
+      const c128* src;
+      if (t < QK_LTX) { int idx = x0 + t; if (idx >= P.Nx) idx = P.Nx - 1; src = P.storeX + (size_t)idx * P.state_stride; }
+      else { int idx = y0 + (t - QK_LTX); if (idx >= P.Ny) idx = P.Ny - 1; src = P.storeY + (size_t)idx * P.state_stride; }
+      const uint32_t dst = qk_smem_u32(stage + ((size_t)buf * NT + t) * BLK + ch);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + off + ch) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  c128 E[DM][DM];
+#pragma unroll
+  for (int a = 0; a < DM; ++a)
+#pragma unroll
+    for (int c = 0; c < DM; ++c) E[a][c] = cmake(0.0, 0.0);
+  E[0][0] = cmake(1.0, 0.0);
+
+  issue(0, 0);
+  const unsigned char* chx = s_chi + tx * (n + 1);
+  const unsigned char* chy = s_chi + (QK_LTX + ty) * (n + 1);
+  for (int s = 0; s < n; ++s) {
+    const int buf = s & 1;
+    if (s + 1 < n) issue(s + 1, buf ^ 1);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    if (active) {
+      const int cxl = chx[s], cxr = chx[s + 1], cyl = chy[s], cyr = chy[s + 1];
+      const c128* Ax = stage + ((size_t)buf * NT + tx) * BLK;
+      const c128* Ay = stage + ((size_t)buf * NT + QK_LTX + ty) * BLK;
+      c128 En[DM][DM];
+#pragma unroll
+      for (int a = 0; a < DM; ++a)
+#pragma unroll
+        for (int c = 0; c < DM; ++c) En[a][c] = cmake(0.0, 0.0);
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+#pragma unroll
+        for (int cp = 0; cp < DM; ++cp) {
+          if (cp < cxr) {
+            c128 t[DM];
+#pragma unroll
+            for (int a = 0; a < DM; ++a) t[a] = cmake(0.0, 0.0);
+#pragma unroll
+            for (int c = 0; c < DM; ++c) {
+              if (c < cxl) {
+                const c128 ax = Ax[(c * 2 + p) * cxr + cp];
+#pragma unroll
+                for (int a = 0; a < DM; ++a) cfma(t[a], E[a][c], ax);     // E is zero beyond (cyl, cxl)
+              }
+            }
+#pragma unroll
+            for (int a = 0; a < DM; ++a) {
+              if (a < cyl) {
+#pragma unroll
+                for (int bp = 0; bp < DM; ++bp) {
+                  if (bp < cyr) cfmac(En[bp][cp], Ay[(a * 2 + p) * cyr + bp], t[a]);
+                }
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < DM; ++a)
+#pragma unroll
+        for (int c = 0; c < DM; ++c) E[a][c] = En[a][c];
+    }
+    __syncthreads();   // everyone is done with `buf` before the next iteration's prefetch overwrites it
+  }
+  if (active) {
+    const double v = E[0][0].x * E[0][0].x + E[0][0].y * E[0][0].y;
+    P.K[(size_t)y * P.ldk + x] = v;
+    if (P.symmetric) P.K[(size_t)x * P.ldk + y] = v;
+  }
+}
+
+template <int DM>
+static cudaError_t launch_lane(const LaneParams& P, cudaStream_t stream) {
+  constexpr int NT = QK_LTX + QK_LTY;
+  constexpr int BLK = DM * 2 * DM + 1;
+  size_t smem = (size_t)2 * NT * BLK * sizeof(c128);
+  smem += (size_t)(P.n + (P.n & 1)) * sizeof(int) + (size_t)P.n * sizeof(int64_t) + (size_t)NT * (P.n + 1);
+  smem = (smem + 15) & ~(size_t)15;
+  cudaError_t e = cudaFuncSetAttribute(qk_gram_lane_kernel<DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  qk_gram_lane_kernel<DM><<<P.n_cta_tiles, QK_LTX * QK_LTY, smem, stream>>>(P);
+  return cudaGetLastError();
+}
+
+cudaError_t qk_launch_gram_lane(const LaneParams& P, int dm, cudaStream_t stream) {
+  if (P.n_cta_tiles <= 0) return cudaSuccess;
+  if (dm <= 2) return launch_lane<2>(P, stream);
+  if (dm <= 4) return launch_lane<4>(P, stream);
   return cudaErrorInvalidValue;
 }
 

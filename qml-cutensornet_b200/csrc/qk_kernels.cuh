@@ -50,6 +50,27 @@ void qk_gram_dmma_tile_shape(int maxD, int* ti, int* tj);
 cudaError_t qk_launch_gram_frag_generic(const GramParams& P, const int2* pairs_dev, int n_pairs, int maxD,
                                         cudaStream_t stream);
 
+// Low-bond-dimension overlap kernel (chi <= 4): one LANE per (bra, ket) pair on the FP64 CUDA cores, reading the
+// unpadded stage-1 stores.  An 8x8x4 DMMA tile is at most 1/4 (chi = 4) or 1/16 (chi = 2) occupied in this regime.
+struct LaneParams {
+  int n;
+  const int32_t* cap;        // device [n+1] bond caps of the plan (slot capacities)
+  const int64_t* site_off;   // device [n+1] slot offsets inside one state, c128 units
+  int64_t state_stride;      // c128 units per state
+  const c128* storeX;
+  const int32_t* chiX;       // device [Nx][n+1]
+  const c128* storeY;
+  const int32_t* chiY;
+  int Nx, Ny;
+  const int4* tiles;         // device [n_cta_tiles]: (y0, x0, y_end, x_end)
+  int n_cta_tiles;
+  int symmetric;
+  double* K;
+  int64_t ldk;
+};
+cudaError_t qk_launch_gram_lane(const LaneParams& P, int dm /* 2 or 4 */, cudaStream_t stream);
+void qk_gram_lane_tile_shape(int* tx, int* ty);
+
 // CUDA-core cross-check on the unpadded stores
 cudaError_t qk_launch_gram_store(int n, const c128* storeX, int64_t strideX, const int64_t* site_off_x,
                                  const int32_t* chiX, int capx, int Nx,

@@ -60,7 +60,7 @@ EXPORTS = [
     "qk_simulate", "qk_simulate_dev", "qk_simulate_trace", "qk_batch_sim_ms", "qk_batch_size", "qk_batch_info", "qk_batch_export",
     "qk_batch_import", "qk_batch_max_chi", "qk_batch_destroy", "qk_frag_stride", "qk_batch_pack",
     "qk_batch_pack_scatter",
-    "qk_gram_frags", "qk_gram_store", "qk_gram_host", "qk_dmma_peak",
+    "qk_gram_frags", "qk_batch_store", "qk_gram_lane", "qk_gram_store", "qk_gram_host", "qk_dmma_peak",
 ]
 
 _lib = None
@@ -232,6 +232,12 @@ class Batch:
         _check(lib().qk_batch_pack_scatter(self._h, _p(D, ctypes.c_int32), ctypes.c_void_p(frag_ptr),
                                            _p(dst, ctypes.c_int32), ctypes.c_void_p(stream)))
 
+    def store(self):
+        """(device pointer of the unpadded store, c128 per state, device pointer of chi [N][n+1] int32)."""
+        ptr, chi, stride = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64()
+        _check(lib().qk_batch_store(self._h, ctypes.byref(ptr), ctypes.byref(stride), ctypes.byref(chi)))
+        return int(ptr.value or 0), int(stride.value), int(chi.value or 0)
+
     def gram_store(self, other=None) -> tuple[np.ndarray, float]:
         """CUDA-core cross-check kernel: K[y, x] with y over ``other`` (or self)."""
         rows = self.N if other is None else other.N
@@ -319,6 +325,18 @@ def gram_frags(device, n_qubits, Dx, fragx_ptr, Nx, Dy, fragy_ptr, Ny, tiles, sy
                                ctypes.c_void_p(fragy_ptr or 0), int(Ny), _p(tiles, ctypes.c_int32),
                                int(tiles.shape[0]), int(bool(symmetric)), ctypes.c_void_p(k_ptr), ctypes.c_int64(ldk),
                                ctypes.byref(ms)))
+    return ms.value
+
+
+def gram_lane(plan: Plan, device, max_chi, storex_ptr, chix_ptr, Nx, storey_ptr, chiy_ptr, Ny, tiles, symmetric, k_ptr, ldk,
+              stream=0) -> float:
+    """Lane-per-pair overlap kernel on the unpadded stores (all bond dimensions <= max_chi <= 4)."""
+    tiles = np.ascontiguousarray(np.asarray(tiles, dtype=np.int32).reshape(-1, 4))
+    ms = ctypes.c_float()
+    _check(lib().qk_gram_lane(plan._h, int(device), ctypes.c_void_p(stream), int(max_chi), ctypes.c_void_p(storex_ptr),
+                              ctypes.c_void_p(chix_ptr), int(Nx), ctypes.c_void_p(storey_ptr or 0),
+                              ctypes.c_void_p(chiy_ptr or 0), int(Ny), _p(tiles, ctypes.c_int32), int(tiles.shape[0]),
+                              int(bool(symmetric)), ctypes.c_void_p(k_ptr), ctypes.c_int64(ldk), ctypes.byref(ms)))
     return ms.value
 
 

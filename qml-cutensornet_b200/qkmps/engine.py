@@ -19,8 +19,21 @@ import time
 
 import numpy as np
 
+import os
+
 from . import (CHI_LIMIT, DMMA_D_LIMIT, QK_FLAG_CAP_HIT, QK_FLAG_NO_CONVERGE, Batch, Plan, QkError, frag_stride,
-               gram_frags, pad_dims, simulate_dev)
+               gram_frags, gram_lane, pad_dims, simulate_dev)
+
+LANE_CHI_LIMIT = 4   # at or below this bond dimension stage 2 runs one lane per pair on the FP64 CUDA cores
+
+
+class _DevView:
+    """Zero-copy uint8 view of raw device memory for torch (CUDA array interface)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 2}
+
 
 ROW_BLOCK = 8   # Gram rows are dealt to ranks in blocks of this many rows (multiple of the kernel's TJ)
 
@@ -216,35 +229,78 @@ def build_gram(comm, plan_factory, n_qubits, X, Y=None, chi_cap=16, device=None,
 
     # ---- exchange: batch-uniform padded dims, pack, all-gather
     t0 = time.perf_counter()
-    Dx = pad_dims(allreduce_max_array(comm, sx.max_chi()))
-    Dy = Dx if symmetric else pad_dims(allreduce_max_array(comm, sy.max_chi()))
-    prof["gram_kernel"] = "qk_gram_dmma_kernel" if int(max(Dx.max(), Dy.max())) <= DMMA_D_LIMIT else \
-        "qk_gram_frag_generic_kernel"   # D > 16: CUDA-core kernel on the same packed buffers (any rank count)
+    # one collective for the per-bond maxima and for "every rank holds its shard as one plain batch"
+    lane_local = sx.single_batch() is not None or sx.n_local == 0
+    if not symmetric:
+        lane_local = lane_local and (sy.single_batch() is not None or sy.n_local == 0) and \
+            (sx.n_local == 0 or sy.n_local == 0 or sy.cap == sx.cap)
+    flag = np.array([0 if lane_local else 1], dtype=np.int32)
+    red = allreduce_max_array(comm, np.concatenate([sx.max_chi(), sy.max_chi() if not symmetric else sx.max_chi(), flag]))
+    nb = n_qubits + 1
+    Dx = pad_dims(red[:nb])
+    Dy = Dx if symmetric else pad_dims(red[nb:2 * nb])
+    max_chi = int(red[:2 * nb].max())
+    use_lane = (max_chi <= LANE_CHI_LIMIT and int(red[-1]) == 0 and os.environ.get("QK_GRAM_LANE", "1") != "0")
     stream = torch.cuda.current_stream().cuda_stream
-
-    def packed(shard, D, n_total):
-        stride = frag_stride(n_qubits, D)
-        per = -(-n_total // size)
-        local = torch.empty(max(per, 1) * stride, dtype=torch.uint8, device=dev)
-        shard.pack(D, local.data_ptr(), stream)
-        if size == 1:
-            return local, stride
-        return allgather_bytes(comm, local), stride
-
-    fx, stride_x = packed(sx, Dx, Nx)
-    fy, stride_y = (fx, stride_x) if symmetric else packed(sy, Dy, Ny)
-    torch.cuda.synchronize()
-    prof["exchange_s"] = time.perf_counter() - t0
-    prof["frag_bytes_per_state"] = (stride_x, stride_y)
-
-    # ---- stage 2 on this rank's row blocks
     K = torch.zeros((Ny, Nx), dtype=torch.float64, device=dev)
     tiles = row_tiles(Ny, Nx, symmetric, size, rank)
     ms = 0.0
-    if tiles:
-        ms = gram_frags(device, n_qubits, Dx, fx.data_ptr(), Nx, None if symmetric else Dy,
-                        None if symmetric else fy.data_ptr(), Ny, tiles, symmetric, K.data_ptr(), Nx, stream)
-        launches += 1
+
+    if use_lane:
+        # bond dimensions <= 4: the unpadded stores themselves are exchanged and read by the lane-per-pair kernel
+        prof["gram_kernel"] = "qk_gram_lane_kernel"
+        plan = sx.plan
+        stride_b = int(plan.info().state_stride) * 16
+
+        def gathered(shard, n_total):
+            b = shard.single_batch()
+            if size == 1:
+                ptr, _, chi_ptr = b.store()
+                return ptr, chi_ptr, None
+            per = -(-n_total // size)
+            st = torch.zeros(max(per, 1) * stride_b, dtype=torch.uint8, device=dev)
+            ch = torch.ones(max(per, 1) * nb, dtype=torch.int32, device=dev)
+            if b is not None and b.N:
+                ptr, _, chi_ptr = b.store()
+                st[:b.N * stride_b].copy_(torch.as_tensor(_DevView(ptr, b.N * stride_b), device=dev))
+                ch[:b.N * nb].copy_(torch.as_tensor(_DevView(chi_ptr, b.N * nb * 4), device=dev).view(torch.int32))
+            st_all, ch_all = allgather_bytes(comm, st), allgather_bytes(comm, ch)
+            return st_all.data_ptr(), ch_all.data_ptr(), (st_all, ch_all)
+
+        px, cx, keep_x = gathered(sx, Nx)
+        py, cy, keep_y = (px, cx, None) if symmetric else gathered(sy, Ny)
+        torch.cuda.synchronize()
+        prof["exchange_s"] = time.perf_counter() - t0
+        prof["frag_bytes_per_state"] = (stride_b, stride_b)
+        if tiles:
+            ms = gram_lane(plan, device, max_chi, px, cx, Nx, None if symmetric else py, None if symmetric else cy, Ny,
+                           tiles, symmetric, K.data_ptr(), Nx, stream)
+            launches += 1
+        del keep_x, keep_y
+    else:
+        prof["gram_kernel"] = "qk_gram_dmma_kernel" if int(max(Dx.max(), Dy.max())) <= DMMA_D_LIMIT else \
+            "qk_gram_frag_generic_kernel"   # D > 16: CUDA-core kernel on the same packed buffers (any rank count)
+
+        def packed(shard, D, n_total):
+            stride = frag_stride(n_qubits, D)
+            per = -(-n_total // size)
+            local = torch.empty(max(per, 1) * stride, dtype=torch.uint8, device=dev)
+            shard.pack(D, local.data_ptr(), stream)
+            if size == 1:
+                return local, stride
+            return allgather_bytes(comm, local), stride
+
+        fx, stride_x = packed(sx, Dx, Nx)
+        fy, stride_y = (fx, stride_x) if symmetric else packed(sy, Dy, Ny)
+        torch.cuda.synchronize()
+        prof["exchange_s"] = time.perf_counter() - t0
+        prof["frag_bytes_per_state"] = (stride_x, stride_y)
+
+        # ---- stage 2 on this rank's row blocks
+        if tiles:
+            ms = gram_frags(device, n_qubits, Dx, fx.data_ptr(), Nx, None if symmetric else Dy,
+                            None if symmetric else fy.data_ptr(), Ny, tiles, symmetric, K.data_ptr(), Nx, stream)
+            launches += 1
     launches += sx.launches + (sy.launches if sy is not None else 0)
     prof["gram_ms"] = ms
     prof["Dx"], prof["Dy"] = Dx, Dy

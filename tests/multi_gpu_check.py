@@ -20,13 +20,16 @@ def main():
     comm = init_from_env("nccl")
     rank, size = comm.Get_rank(), comm.Get_size()
     worst = 0.0
+    kernels = set()
     for (n, r, g, d, nx, ny) in [(10, 2, 0.5, 1, 40, 13), (12, 2, 0.7, 2, 37, 9), (14, 2, 0.1, 2, 21, 21), (10, 3, 0.5, 4, 10, 6)]:
         emap = oracle.entanglement_graph(n, d)
         X = oracle.synthetic_features(nx, n, 0)
         Y = oracle.synthetic_features(ny, n, 1)
         ans = KernelStateAnsatz(n, r, g, emap)
         K = build_kernel_matrix(comm, ans, X, truncation_error=1e-16)
+        kernels.add(build_kernel_matrix.last_profile["gram_kernel"])
         Kt = build_kernel_matrix(comm, ans, X, Y, truncation_error=1e-16)
+        kernels.add(build_kernel_matrix.last_profile["gram_kernel"])
         if rank == 0:
             e1 = np.abs(K - oracle.statevector_gram(n, r, g, emap, X)).max()
             e2 = np.abs(Kt - oracle.statevector_gram(n, r, g, emap, X, Y)).max()
@@ -41,6 +44,8 @@ def main():
     comm.Barrier()
     if rank == 0:
         assert worst < 1e-8, worst
+        # both stage-2 paths were exercised across ranks: stores (chi <= 4) and packed fragments
+        assert {"qk_gram_lane_kernel", "qk_gram_dmma_kernel"} <= kernels, kernels
         print(f"MULTI_GPU_OK ranks={size} max_err={worst:.3e}")
 
 

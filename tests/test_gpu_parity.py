@@ -355,3 +355,33 @@ def test_large_bond_dimension_path(qk, cuda_device):
     assert np.array_equal(K, K.T)
     Kt = build_kernel_matrix(SingleComm(), ans, X, Y, info_file="/tmp/qk_big", truncation_error=1e-16)
     assert np.abs(Kt - oracle.statevector_gram(n, r, g, emap, X, Y)).max() < TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,r,g,d,nx,ny", [(16, 2, 0.1, 1, 45, 19),     # chi <= 2: DM = 2 instantiation
+                                           (20, 2, 0.5, 1, 37, 23),     # chi <= 4 (BASELINE config 2 shape)
+                                           (12, 2, 0.9, 1, 17, 17),
+                                           (9, 2, 0.7, 1, 1, 1)])
+def test_low_chi_lane_kernel(qk, cuda_device, monkeypatch, n, r, g, d, nx, ny):
+    """Bond dimensions <= 4 take the lane-per-pair CUDA-core kernel on the unpadded stores: same Gram as the exact
+    statevector (1e-8), as the tensor-core kernel on the packed fragments (1e-12) and exactly symmetric; ragged
+    tile edges (sizes that are not multiples of the 16 x 8 CTA tile) and a rectangular test Gram included."""
+    from gpu_backend.kernel_state_ansatz import build_kernel_matrix
+    from qkmps.engine import SingleComm
+    emap = oracle.entanglement_graph(n, d)
+    X = oracle.synthetic_features(nx, n, 3)
+    Y = oracle.synthetic_features(ny, n, 4)
+    ans = _ansatz(n, r, g, d)
+    K = build_kernel_matrix(SingleComm(), ans, X, truncation_error=1e-16)
+    assert build_kernel_matrix.last_profile["gram_kernel"] == "qk_gram_lane_kernel"
+    assert int(build_kernel_matrix.last_profile["info_x"]["chi"].max()) <= 4
+    Kt = build_kernel_matrix(SingleComm(), ans, X, Y, truncation_error=1e-16)
+    assert build_kernel_matrix.last_profile["gram_kernel"] == "qk_gram_lane_kernel"
+    assert np.array_equal(K, K.T)
+    assert np.abs(K - oracle.statevector_gram(n, r, g, emap, X)).max() < TOL
+    assert np.abs(Kt - oracle.statevector_gram(n, r, g, emap, X, Y)).max() < TOL
+    monkeypatch.setenv("QK_GRAM_LANE", "0")
+    K2 = build_kernel_matrix(SingleComm(), ans, X, truncation_error=1e-16)
+    assert build_kernel_matrix.last_profile["gram_kernel"] == "qk_gram_dmma_kernel"
+    Kt2 = build_kernel_matrix(SingleComm(), ans, X, Y, truncation_error=1e-16)
+    assert np.abs(K - K2).max() < 1e-12 and np.abs(Kt - Kt2).max() < 1e-12
