@@ -485,7 +485,8 @@ cudaError_t qk_launch_gram_dmma(const GramParams& P, int maxD, cudaStream_t stre
 // CTA = 16 kets x 8 bras = 128 threads; thread (tx, ty) owns the pair and keeps its transfer matrix E (DM x DM
 // complex) in registers for the whole sweep.  Per site the live prefix of the 24 site tensors involved
 // (<= DM*2*DM c128 each, straight from the stage-1 store) is double-buffered into shared memory with 16-byte
-// cp.async; blocks are skewed by 16 B so that the 16 kets of a warp hit different banks.
+// cp.async, then re-laid out once per CTA into zero-padded [DM][2][DM] blocks (skewed by 16 B so that the 16
+// kets of a warp hit different banks): the per-lane arithmetic is then fully unrolled with no guards.
 //   t[a]      = sum_c  E[a][c] A_x[c][p][c']                 (for each p, c')
 //   E'[b'][c'] += sum_a conj(A_y[a][p][b']) t[a]
 // 8 DM^3 complex MACs per pair and site, all on the FP64 FMA pipe: 64 lanes/clk/SM.
@@ -495,13 +496,15 @@ cudaError_t qk_launch_gram_dmma(const GramParams& P, int maxD, cudaStream_t stre
 void qk_gram_lane_tile_shape(int* tx, int* ty) { *tx = QK_LTX; *ty = QK_LTY; }
 
 template <int DM>
-__global__ void __launch_bounds__(QK_LTX * QK_LTY, 3) qk_gram_lane_kernel(const __grid_constant__ LaneParams P) {
+__global__ void __launch_bounds__(QK_LTX * QK_LTY, DM > 2 ? 2 : 4) qk_gram_lane_kernel(const __grid_constant__ LaneParams P) {
   constexpr int NT = QK_LTX + QK_LTY;
-  constexpr int BLK = DM * 2 * DM + 1;               // c128 per staged block (+1: bank skew)
+  constexpr int RAW = DM * 2 * DM;                    // c128 copied per state and site (live prefix of the slot)
+  constexpr int BLK = DM * 2 * DM + 1;                // c128 per zero-padded block (+1: bank skew)
   extern __shared__ __align__(16) unsigned char lsm[];
   const int n = P.n;
-  c128* stage = (c128*)lsm;                           // [2][NT][BLK]
-  int* s_len = (int*)(stage + 2 * NT * BLK);          // [n]   c128 copied per state at site s
+  c128* raw = (c128*)lsm;                             // [2][NT][RAW]   as stored: [chi_l][2][chi_r], current dims
+  c128* pad = raw + 2 * NT * RAW;                     // [NT][BLK]      re-laid out as [DM][2][DM], zero outside
+  int* s_len = (int*)(pad + NT * BLK);                // [n]   c128 copied per state at site s
   int64_t* s_off = (int64_t*)(s_len + n + (n & 1));   // [n]
   unsigned char* s_chi = (unsigned char*)(s_off + n); // [NT][n+1]
   const int tid = threadIdx.x;
@@ -513,7 +516,7 @@ __global__ void __launch_bounds__(QK_LTX * QK_LTY, 3) qk_gram_lane_kernel(const 
 
   for (int s = tid; s < n; s += blockDim.x) {
     const int full = P.cap[s] * 2 * P.cap[s + 1];
-    s_len[s] = full < DM * 2 * DM ? full : DM * 2 * DM;
+    s_len[s] = full < RAW ? full : RAW;
     s_off[s] = P.site_off[s];
   }
   for (int i = tid; i < NT * (n + 1); i += blockDim.x) {
@@ -534,7 +537,7 @@ __global__ void __launch_bounds__(QK_LTX * QK_LTY, 3) qk_gram_lane_kernel(const 
       const c128* src;
       if (t < QK_LTX) { int idx = x0 + t; if (idx >= P.Nx) idx = P.Nx - 1; src = P.storeX + (size_t)idx * P.state_stride; }
       else { int idx = y0 + (t - QK_LTX); if (idx >= P.Ny) idx = P.Ny - 1; src = P.storeY + (size_t)idx * P.state_stride; }
-      const uint32_t dst = qk_smem_u32(stage + ((size_t)buf * NT + t) * BLK + ch);
+      const uint32_t dst = qk_smem_u32(raw + ((size_t)buf * NT + t) * RAW + ch);
       asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + off + ch) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -548,18 +551,25 @@ __global__ void __launch_bounds__(QK_LTX * QK_LTY, 3) qk_gram_lane_kernel(const 
   E[0][0] = cmake(1.0, 0.0);
 
   issue(0, 0);
-  const unsigned char* chx = s_chi + tx * (n + 1);
-  const unsigned char* chy = s_chi + (QK_LTX + ty) * (n + 1);
   for (int s = 0; s < n; ++s) {
     const int buf = s & 1;
     if (s + 1 < n) issue(s + 1, buf ^ 1);
     else asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();                                   // site s has landed; everyone is done with `pad`
+    // zero-padded fixed-shape copy: the arithmetic below then needs no guard on the per-lane bond dimensions
+    for (int i = tid; i < NT * RAW; i += blockDim.x) {
+      const int t = i / RAW, e = i - t * RAW;
+      const int c = e / (2 * DM), p = (e / DM) & 1, cp = e % DM;
+      const int cl = s_chi[t * (n + 1) + s], cr = s_chi[t * (n + 1) + s + 1];
+      c128 v = cmake(0.0, 0.0);
+      if (c < cl && cp < cr) v = raw[((size_t)buf * NT + t) * RAW + (c * 2 + p) * cr + cp];
+      pad[(size_t)t * BLK + e] = v;
+    }
     __syncthreads();
     if (active) {
-      const int cxl = chx[s], cxr = chx[s + 1], cyl = chy[s], cyr = chy[s + 1];
-      const c128* Ax = stage + ((size_t)buf * NT + tx) * BLK;
-      const c128* Ay = stage + ((size_t)buf * NT + QK_LTX + ty) * BLK;
+      const c128* Ax = pad + (size_t)tx * BLK;
+      const c128* Ay = pad + (size_t)(QK_LTX + ty) * BLK;
       c128 En[DM][DM];
 #pragma unroll
       for (int a = 0; a < DM; ++a)
@@ -569,27 +579,19 @@ __global__ void __launch_bounds__(QK_LTX * QK_LTY, 3) qk_gram_lane_kernel(const 
       for (int p = 0; p < 2; ++p) {
 #pragma unroll
         for (int cp = 0; cp < DM; ++cp) {
-          if (cp < cxr) {
-            c128 t[DM];
+          c128 t[DM];
 #pragma unroll
-            for (int a = 0; a < DM; ++a) t[a] = cmake(0.0, 0.0);
+          for (int a = 0; a < DM; ++a) t[a] = cmake(0.0, 0.0);
 #pragma unroll
-            for (int c = 0; c < DM; ++c) {
-              if (c < cxl) {
-                const c128 ax = Ax[(c * 2 + p) * cxr + cp];
+          for (int c = 0; c < DM; ++c) {
+            const c128 ax = Ax[(c * 2 + p) * DM + cp];
 #pragma unroll
-                for (int a = 0; a < DM; ++a) cfma(t[a], E[a][c], ax);     // E is zero beyond (cyl, cxl)
-              }
-            }
+            for (int a = 0; a < DM; ++a) cfma(t[a], E[a][c], ax);
+          }
 #pragma unroll
-            for (int a = 0; a < DM; ++a) {
-              if (a < cyl) {
+          for (int a = 0; a < DM; ++a) {
 #pragma unroll
-                for (int bp = 0; bp < DM; ++bp) {
-                  if (bp < cyr) cfmac(En[bp][cp], Ay[(a * 2 + p) * cyr + bp], t[a]);
-                }
-              }
-            }
+            for (int bp = 0; bp < DM; ++bp) cfmac(En[bp][cp], Ay[(a * 2 + p) * DM + bp], t[a]);
           }
         }
       }
@@ -598,7 +600,6 @@ __global__ void __launch_bounds__(QK_LTX * QK_LTY, 3) qk_gram_lane_kernel(const 
 #pragma unroll
         for (int c = 0; c < DM; ++c) E[a][c] = En[a][c];
     }
-    __syncthreads();   // everyone is done with `buf` before the next iteration's prefetch overwrites it
   }
   if (active) {
     const double v = E[0][0].x * E[0][0].x + E[0][0].y * E[0][0].y;
@@ -610,8 +611,8 @@ __global__ void __launch_bounds__(QK_LTX * QK_LTY, 3) qk_gram_lane_kernel(const 
 template <int DM>
 static cudaError_t launch_lane(const LaneParams& P, cudaStream_t stream) {
   constexpr int NT = QK_LTX + QK_LTY;
-  constexpr int BLK = DM * 2 * DM + 1;
-  size_t smem = (size_t)2 * NT * BLK * sizeof(c128);
+  constexpr int RAW = DM * 2 * DM, BLK = RAW + 1;
+  size_t smem = (size_t)(2 * NT * RAW + NT * BLK) * sizeof(c128);
   smem += (size_t)(P.n + (P.n & 1)) * sizeof(int) + (size_t)P.n * sizeof(int64_t) + (size_t)NT * (P.n + 1);
   smem = (smem + 15) & ~(size_t)15;
   cudaError_t e = cudaFuncSetAttribute(qk_gram_lane_kernel<DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
