@@ -276,11 +276,12 @@ def run_ours(args):
     gates = ans.ansatz_circ.get_commands()
     plans = {}
 
-    def plan_factory(cap, early_exit=False):
-        key = (cap, bool(early_exit))
+    def plan_factory(cap, early_exit=False, parallel=False):
+        key = (cap, bool(early_exit), bool(parallel))
         if key not in plans:
             plans[key] = qkmps.Plan(n, gates, qkmps.QK_TRUNC_PYTKET, 1e-16, cap,
-                                    qkmps.QK_PLAN_EARLY_EXIT if early_exit else 0)
+                                    (qkmps.QK_PLAN_EARLY_EXIT if early_exit else 0) |
+                                    (qkmps.QK_PLAN_PARALLEL if parallel else 0))
         return plans[key]
 
     from gpu_backend.kernel_state_ansatz import _initial_cap

@@ -67,6 +67,8 @@ typedef enum {
 
 #define QK_PLAN_NO_FUSION 4       /* keep one SVD per 2-qubit gate (default: gates that follow each other on the
                                      same bond are multiplied into one SVD and SWAP pairs cancel) */
+#define QK_PLAN_PARALLEL 8        /* stage 1 in B (Vidal/Hastings) form: no gauge moves; ops levelised by the sites
+                                     they touch so that independent bonds of one datapoint are updated concurrently */
 
 typedef struct qk_plan qk_plan;     /* compiled static op schedule of one ansatz (host object) */
 typedef struct qk_batch qk_batch;   /* device-resident batch of simulated MPS */

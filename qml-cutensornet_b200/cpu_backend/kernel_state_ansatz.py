@@ -22,7 +22,7 @@ _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if _PKG_ROOT not in sys.path:
     sys.path.insert(0, _PKG_ROOT)
 
-from qkmps import QK_PLAN_EARLY_EXIT, QK_TRUNC_ITENSORS, Plan  # noqa: E402
+from qkmps import QK_PLAN_EARLY_EXIT, QK_PLAN_PARALLEL, QK_TRUNC_ITENSORS, Plan  # noqa: E402
 from qkmps.ansatz import KernelStateAnsatzBase, expected_chi, structural_chi_bound  # noqa: E402
 from qkmps.comm import Wtime  # noqa: E402
 from qkmps.engine import build_gram  # noqa: E402
@@ -65,11 +65,11 @@ def build_kernel_matrix(mpi_comm, ansatz, X, Y=None, info_file="info_file", trun
     # compiled schedules are kept on the ansatz: the train and the test kernel of one run share them
     plans = ansatz.__dict__.setdefault("_qk_plans", {})
 
-    def plan_factory(cap, early_exit=False):
-        key = (QK_TRUNC_ITENSORS, float(truncation_error), cap, bool(early_exit), os.environ.get("QK_SCHEDULE", ""))
+    def plan_factory(cap, early_exit=False, parallel=False):
+        key = (QK_TRUNC_ITENSORS, float(truncation_error), cap, bool(early_exit), bool(parallel), os.environ.get("QK_SCHEDULE", ""))
         if key not in plans:
             plans[key] = Plan(n_qubits, gates, QK_TRUNC_ITENSORS, float(truncation_error), cap,
-                              QK_PLAN_EARLY_EXIT if early_exit else 0)
+                              (QK_PLAN_EARLY_EXIT if early_exit else 0) | (QK_PLAN_PARALLEL if parallel else 0))
         return plans[key]
 
     if chi is not None:

@@ -9,6 +9,10 @@
 cudaError_t qk_launch_sim(const SimParams& P, int G, size_t smem_bytes, int* work_counter, cudaStream_t stream,
                           int* grid_out);
 
+// B-form kernel: one cluster of `ncta` CTAs per datapoint; parts = device scratch [N][ncta] QkStat
+cudaError_t qk_launch_sim_b(const SimParams& P, int G, size_t smem_bytes, int ncta, QkStat* parts, cudaStream_t stream,
+                            int* grid_out);
+
 // ---- exchange format ("frag") ----
 // Per state: for every site s a block of Dl*Dr*4 doubles in DMMA A-fragment order, then n+1 bytes
 // (padded to 16) holding ceil(chi_b / 8) per bond.  See DESIGN.md "Data layout".

@@ -123,6 +123,9 @@ int qk_compile_plan(int n, const qk_gate* gates_in, int n_gates, int trunc_mode,
   plan->reorder = (flags & QK_PLAN_LITERAL_ORDER) ? 0 : 1;
   plan->early_exit = (flags & QK_PLAN_EARLY_EXIT) ? 1 : 0;
   plan->fuse = (flags & QK_PLAN_NO_FUSION) ? 0 : 1;
+  plan->parallel = (flags & QK_PLAN_PARALLEL) ? 1 : 0;
+  if (plan->parallel) plan->reorder = 0;   // the literal order has the shallow dependency graph (C3: depth 28)
+  plan->level_start.clear();
   if (n < 1) { *err = "n_qubits must be >= 1"; return QK_ERR_ARG; }
   if (n_gates < 0 || (n_gates > 0 && !gates_in)) { *err = "bad gate list"; return QK_ERR_ARG; }
   if (trunc_mode != QK_TRUNC_ITENSORS && trunc_mode != QK_TRUNC_PYTKET) { *err = "bad truncation mode"; return QK_ERR_ARG; }
@@ -164,7 +167,7 @@ int qk_compile_plan(int n, const qk_gate* gates_in, int n_gates, int trunc_mode,
   for (int i = 0; i < n_gates; ++i) {
     const qk_gate& g = gates[i];
     const bool two = (g.kind == QK_GATE_XX || g.kind == QK_GATE_ZZ || g.kind == QK_GATE_SWAP);
-    if (two && plan->reorder && plan->fuse && !items.empty() && items.back().two && items.back().k == g.q0 &&
+    if (two && (plan->reorder || plan->parallel) && plan->fuse && !items.empty() && items.back().two && items.back().k == g.q0 &&
         items.back().g.size() < kMaxFuse) {
       std::vector<qk_gate>& grp = items.back().g;
       if (g.kind == QK_GATE_SWAP && grp.back().kind == QK_GATE_SWAP) {
@@ -186,8 +189,40 @@ int qk_compile_plan(int n, const qk_gate* gates_in, int n_gates, int trunc_mode,
     if (items[i].two) nxt = items[i].k;
   }
 
+  if (plan->parallel) {
+    // B form needs no orthogonality centre: an item only depends on the earlier items that touch its site(s).
+    // Level = longest such chain; items of one level act on disjoint sites and may run concurrently.
+    std::vector<int> ready(n, 0), level(n_items, 0);
+    int n_levels = 0;
+    for (int i = 0; i < n_items; ++i) {
+      const Item& it = items[i];
+      int lv = ready[it.k];
+      if (it.two && ready[it.k + 1] > lv) lv = ready[it.k + 1];
+      level[i] = lv;
+      ready[it.k] = lv + 1;
+      if (it.two) ready[it.k + 1] = lv + 1;
+      if (lv + 1 > n_levels) n_levels = lv + 1;
+    }
+    plan->level_start.assign(n_levels + 1, 0);
+    for (int lv = 0; lv < n_levels; ++lv) {
+      plan->level_start[lv] = (int32_t)plan->ops.size();
+      for (int i = 0; i < n_items; ++i) {
+        if (level[i] != lv) continue;
+        const Item& it = items[i];
+        const int ng = (int)it.g.size();
+        for (int j = 0; j < ng; ++j) {
+          const qk_gate& g = it.g[j];
+          QkOp op; op.kind = g.kind; op.site = it.k; op.fa = g.fa; op.fb = g.fb; op.dir = lv; op.coeff = g.coeff;
+          op.pad = it.two ? ((j + 1 < ng ? QK_OPF_CONT : 0) | (j > 0 ? QK_OPF_ACC : 0)) : 0;
+          plan->ops.push_back(op);
+        }
+        if (it.two) plan->n_2q++; else plan->n_1q++;
+      }
+    }
+    plan->level_start[n_levels] = (int32_t)plan->ops.size();
+  }
   int centre = -1;   // -1: product state, every site is both left- and right-orthonormal
-  for (int i = 0; i < n_items; ++i) {
+  for (int i = 0; i < n_items && !plan->parallel; ++i) {
     const Item& it = items[i];
     if (!it.two) {
       const qk_gate& g = it.g[0];

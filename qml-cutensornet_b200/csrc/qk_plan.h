@@ -22,6 +22,8 @@ struct qk_plan {
   int reorder = 1;                 // commutation-aware reordering of interaction runs (qk_plan.cpp)
   int early_exit = 0;              // QK_PLAN_EARLY_EXIT
   int fuse = 1;                    // fuse consecutive 2-qubit gates on one bond (off: QK_PLAN_NO_FUSION)
+  int parallel = 0;                // QK_PLAN_PARALLEL: B form, levelised ops
+  std::vector<int32_t> level_start;  // [n_levels + 1] (parallel plans)
 };
 
 // Returns 0 or a negative qk_status; err receives a message.

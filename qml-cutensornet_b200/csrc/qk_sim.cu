@@ -7,7 +7,11 @@
 // stays L2-resident (working set = resident CTAs x one MPS, far below the 126 MB L2); HBM sees the
 // final state once.  Datapoints are handed out through an atomic counter so ragged bond dimensions
 // do not leave SMs idle.
+#include <cooperative_groups.h>
+#include <stdlib.h>
 #include "qk_kernels.cuh"
+// level barrier of the B-form path: the CTAs of one thread-block cluster share a datapoint
+#define QK_GROUP_SYNC() do { __threadfence(); cooperative_groups::this_cluster().sync(); __threadfence(); } while (0)
 #include "qk_sim_core.h"
 
 // resident CTAs per SM the register allocation is sized for (shared memory allows 6 at chi_cap 16)
@@ -56,6 +60,60 @@ cudaError_t qk_launch_sim(const SimParams& P, int G, size_t smem_bytes, int* wor
     case 64: return launch_g<64>(P, smem_bytes, work_counter, stream, grid_out);
     case 128: return launch_g<128>(P, smem_bytes, work_counter, stream, grid_out);
     case 256: return launch_g<256>(P, smem_bytes, work_counter, stream, grid_out);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// B-form kernel (QK_PLAN_PARALLEL): one thread-block CLUSTER per datapoint.  The ops of a level touch
+// disjoint sites, so the cluster's CTAs take them round-robin and meet at a cluster barrier between levels;
+// the dependency depth of the ansatz (C3: 28 levels for 386 two-qubit ops) replaces the op count as the
+// latency of one datapoint.  State, bond dimensions and Schmidt values live in global memory (L2).
+// ------------------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(G, SimMinBlocks<G>::value) qk_sim_kernel_b(const __grid_constant__ SimParams P, QkStat* parts) {
+  extern __shared__ __align__(16) unsigned char qk_smem[];
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int ncta = (int)cluster.num_blocks();
+  const int cta = (int)cluster.block_rank();
+  const int n_clusters = (int)(gridDim.x / ncta);
+  SimCtx c;
+  qk_sim_carve(c, &P, qk_smem, G);
+  for (int dp = (int)(blockIdx.x / ncta); dp < P.N; dp += n_clusters) {
+    qk_sim_datapoint_b<G>(c, dp, cta, ncta, parts + (size_t)dp * ncta);
+    QK_GROUP_SYNC();
+  }
+}
+
+template <int G>
+static cudaError_t launch_b(const SimParams& P, size_t smem, int ncta, QkStat* parts, cudaStream_t stream, int* grid_out) {
+  cudaError_t e = cudaFuncSetAttribute(qk_sim_kernel_b<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)ncta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(G); cfg.dynamicSmemBytes = smem; cfg.stream = stream; cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.gridDim = dim3((unsigned)ncta);
+  int max_clusters = 0;
+  e = cudaOccupancyMaxActiveClusters(&max_clusters, qk_sim_kernel_b<G>, &cfg);
+  if (e != cudaSuccess) return e;
+  if (max_clusters < 1) return cudaErrorInvalidConfiguration;
+  long long clusters = max_clusters < P.N ? max_clusters : P.N;
+  if (clusters < 1) clusters = 1;
+  cfg.gridDim = dim3((unsigned)(clusters * ncta));
+  if (grid_out) *grid_out = (int)(clusters * ncta);
+  return cudaLaunchKernelEx(&cfg, qk_sim_kernel_b<G>, P, parts);
+}
+
+cudaError_t qk_launch_sim_b(const SimParams& P, int G, size_t smem_bytes, int ncta, QkStat* parts, cudaStream_t stream,
+                            int* grid_out) {
+  switch (G) {
+    case 32: return launch_b<32>(P, smem_bytes, ncta, parts, stream, grid_out);
+    case 64: return launch_b<64>(P, smem_bytes, ncta, parts, stream, grid_out);
+    case 128: return launch_b<128>(P, smem_bytes, ncta, parts, stream, grid_out);
+    case 256: return launch_b<256>(P, smem_bytes, ncta, parts, stream, grid_out);
     default: return cudaErrorInvalidValue;
   }
 }

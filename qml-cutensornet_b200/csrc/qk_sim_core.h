@@ -71,6 +71,7 @@ struct SimCtx {
   double* x;      // [n] features of the current datapoint
   SimShared* sh;
   c128* state;    // global: this datapoint's site slots
+  double* lam;    // global: this datapoint's bond weights [(n+1)][lam_ld] (B form only)
 };
 
 // bytes of shared memory the core needs for group size G
@@ -736,6 +737,269 @@ QK_DEV void qk_op_2q(SimCtx& c, const QkOp& op) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// B form (QK_PLAN_PARALLEL).  Every site tensor is kept right-orthonormal (B_k = Gamma_k Lambda_k) and the
+// Schmidt values Lambda_b of every bond are stored next to the state, so that
+//     theta = Lambda_{k-1} * gate * (B_k B_{k+1})
+// is the orthogonality-centre tensor of bond k without any gauge move, and updates of bonds that share no
+// site are independent (Vidal's TEBD form; the update below is Hastings' division-free variant):
+//     theta = U S V^dag ,   B'_{k+1} = V^dag ,   B'_k = (gate * (B_k B_{k+1})) V ,   Lambda'_k = S (renormalised)
+// Same truncation rules on the same Schmidt spectrum as the sequential form; results differ at the level
+// of the truncated weights (1e-16).
+// ------------------------------------------------------------------------------------------------
+// out[(a,L)][t] = s_t sum_{l,b} A[a,l,b] F[t,L,l,b],  F[t,L,l,b] = sum_{R,r} g[(L,R),(l,r)] sum_c B[b,r,c] X[(R,c),t]
+// with X[(R,c),t] = src[(R*cc + c) + col(t) * sT] (conjugated if conj_src); s_t = 1 or 1/sigma_t.
+template <int G>
+QK_DEV void qk_half_left(SimCtx& c, const c128* A, const c128* B, int ca, int cb, int cc, int keep, const c128* src,
+                         int sT, bool use_order, bool conj_src, bool scale_isg, c128* out) {
+  const int m = 2 * ca;
+  int TT = G / cb;
+  if (TT < 1) TT = 1;
+  for (int t0 = 0; t0 < keep; t0 += TT) {
+    QK_PAR_BEGIN(tid)
+      for (int u = tid; u < TT * cb; u += G) {
+        const int tt = u / cb, b = u - tt * cb;
+        const int t = t0 + tt;
+        if (t < keep) {
+          const c128* w = src + (size_t)(use_order ? c.order[t] : t) * sT;
+          c128 e[4];
+          e[0] = e[1] = e[2] = e[3] = cmake(0, 0);
+          const c128* b0 = B + (size_t)(b * 2) * cc;
+          const c128* b1 = b0 + cc;
+          for (int cidx = 0; cidx < cc; ++cidx) {
+            c128 w0 = w[cidx], w1 = w[cc + cidx];
+            if (conj_src) { w0 = cconj(w0); w1 = cconj(w1); }
+            const c128 v0 = b0[cidx], v1 = b1[cidx];
+            cfma(e[0], v0, w0); cfma(e[1], v1, w0);       // e[R*2+r] += B[b,r,c] X[(R,c),t]
+            cfma(e[2], v0, w1); cfma(e[3], v1, w1);
+          }
+          c128* f = c.ef + (size_t)u * 4;
+          for (int L = 0; L < 2; ++L)
+            for (int l = 0; l < 2; ++l) {
+              c128 acc = cmake(0, 0);
+              for (int Rr = 0; Rr < 2; ++Rr)
+                for (int r = 0; r < 2; ++r) cfma(acc, c.gate[(L * 2 + Rr) * 4 + (l * 2 + r)], e[Rr * 2 + r]);
+              f[L * 2 + l] = acc;
+            }
+        }
+      }
+    QK_PAR_END
+    QK_PAR_BEGIN(tid)
+      for (int idx = tid; idx < TT * m; idx += G) {
+        const int tt = idx / m, row = idx - tt * m;
+        const int t = t0 + tt;
+        if (t < keep) {
+          const int a = row >> 1, L = row & 1;
+          const c128* f = c.ef + (size_t)tt * cb * 4 + L * 2;
+          c128 acc = cmake(0, 0);
+          for (int b = 0; b < cb; ++b) {
+            cfma(acc, A[(size_t)(a * 2) * cb + b], f[(size_t)b * 4]);
+            cfma(acc, A[(size_t)(a * 2 + 1) * cb + b], f[(size_t)b * 4 + 1]);
+          }
+          out[(size_t)row * keep + t] = scale_isg ? cscale(acc, c.diag[t].y) : acc;
+        }
+      }
+    QK_PAR_END
+  }
+}
+
+// out[t][(R,c)] = isg_t^2 sum_{r,b} F[t,R,r,b] B[b,r,c],  F[t,R,r,b] = sum_{L,l} g[(L,R),(l,r)] sum_a conj(W[(a,L),col(t)]) lam[a] A[a,l,b]
+template <int G>
+QK_DEV void qk_half_right(SimCtx& c, const c128* A, const double* lam, const c128* B, int ca, int cb, int cc, int keep,
+                          const c128* W, int ldw, bool use_order, c128* out) {
+  const int n2 = 2 * cc;
+  int TT = G / cb;
+  if (TT < 1) TT = 1;
+  for (int t0 = 0; t0 < keep; t0 += TT) {
+    QK_PAR_BEGIN(tid)
+      for (int u = tid; u < TT * cb; u += G) {
+        const int tt = u / cb, b = u - tt * cb;
+        const int t = t0 + tt;
+        if (t < keep) {
+          const c128* w = W + (size_t)(use_order ? c.order[t] : t) * ldw;
+          c128 e[4];
+          e[0] = e[1] = e[2] = e[3] = cmake(0, 0);
+          for (int a = 0; a < ca; ++a) {
+            const double la = lam[a];
+            const c128 w0 = cscale(w[a * 2], la), w1 = cscale(w[a * 2 + 1], la);
+            const c128 a0 = A[(size_t)(a * 2) * cb + b], a1 = A[(size_t)(a * 2 + 1) * cb + b];
+            cfmac(e[0], w0, a0); cfmac(e[1], w0, a1);     // e[L*2+l] += conj(W[(a,L),t]) lam_a A[a,l,b]
+            cfmac(e[2], w1, a0); cfmac(e[3], w1, a1);
+          }
+          c128* f = c.ef + (size_t)u * 4;
+          for (int Rr = 0; Rr < 2; ++Rr)
+            for (int r = 0; r < 2; ++r) {
+              c128 acc = cmake(0, 0);
+              for (int L = 0; L < 2; ++L)
+                for (int l = 0; l < 2; ++l) cfma(acc, c.gate[(L * 2 + Rr) * 4 + (l * 2 + r)], e[L * 2 + l]);
+              f[Rr * 2 + r] = acc;
+            }
+        }
+      }
+    QK_PAR_END
+    QK_PAR_BEGIN(tid)
+      for (int idx = tid; idx < TT * n2; idx += G) {
+        const int tt = idx / n2, col = idx - tt * n2;
+        const int t = t0 + tt;
+        if (t < keep) {
+          const int Rr = col / cc, cidx = col - Rr * cc;
+          const c128* f = c.ef + (size_t)tt * cb * 4 + Rr * 2;
+          c128 acc = cmake(0, 0);
+          for (int b = 0; b < cb; ++b) {
+            cfma(acc, f[(size_t)b * 4], B[(size_t)(b * 2) * cc + cidx]);
+            cfma(acc, f[(size_t)b * 4 + 1], B[(size_t)(b * 2 + 1) * cc + cidx]);
+          }
+          const double isg = c.diag[t].y;
+          out[(size_t)t * n2 + col] = cscale(acc, isg * isg);
+        }
+      }
+    QK_PAR_END
+  }
+}
+
+template <int G>
+QK_DEV void qk_op_2q_b(SimCtx& c, const QkOp& op) {
+  if (op.pad & QK_OPF_CONT) {   // not the last gate of a fused group: only accumulate its matrix
+    QK_PAR_BEGIN(tid)
+      if (tid == 0) {
+        qk_build_gate_2q_fused(op, c.x, c.gate, c.gacc, (c128*)c.scr);
+        for (int i = 0; i < 16; ++i) c.gacc[i] = c.gate[i];
+      }
+    QK_PAR_END
+    return;
+  }
+  const int k = op.site;
+  const int ca = c.chi[k], cb = c.chi[k + 1], cc = c.chi[k + 2];
+  const int m = 2 * ca, n2 = 2 * cc;
+  const bool transposed = (m <= n2);   // ties go to the orientation that needs one half contraction, not two
+  const int R = transposed ? n2 : m;
+  const int C = transposed ? m : n2;
+  const int ldw = R;
+  c128* A = qk_site(c, k);
+  c128* B = qk_site(c, k + 1);
+  c128* W = c.W;
+  const int lam_ld = c.P->lam_ld;
+  const double* lamL = c.lam + (size_t)k * lam_ld;          // Schmidt values of the bond left of site k
+  double* lamM = c.lam + (size_t)(k + 1) * lam_ld;          // bond (k, k+1): rewritten
+
+  QK_PAR_BEGIN(tid)
+    if (tid == 0) qk_build_gate_2q_fused(op, c.x, c.gate, c.gacc, (c128*)c.scr);
+  QK_PAR_END
+
+  // theta[(a,L),(R,c)] = lam[a] sum_{l,r} g[(L,R),(l,r)] sum_b A[a,l,b] B[b,r,c]
+  QK_PAR_BEGIN(tid)
+    for (int idx = tid; idx < ca * cc; idx += G) {
+      const int a = idx / cc, cidx = idx - a * cc;
+      const double la = lamL[a];
+      c128 t[4];
+      for (int l = 0; l < 2; ++l)
+        for (int r = 0; r < 2; ++r) {
+          c128 acc = cmake(0, 0);
+          const c128* ap = A + (size_t)(a * 2 + l) * cb;
+          const c128* bp = B + (size_t)r * cc + cidx;
+          for (int b = 0; b < cb; ++b) cfma(acc, ap[b], bp[(size_t)b * 2 * cc]);
+          t[l * 2 + r] = cscale(acc, la);
+        }
+      for (int L = 0; L < 2; ++L)
+        for (int Rr = 0; Rr < 2; ++Rr) {
+          c128 acc = cmake(0, 0);
+          const c128* g = c.gate + (L * 2 + Rr) * 4;
+          for (int lr = 0; lr < 4; ++lr) cfma(acc, g[lr], t[lr]);
+          const int row = a * 2 + L, col = Rr * cc + cidx;
+          if (!transposed) W[row + (size_t)col * ldw] = acc;
+          else W[col + (size_t)row * ldw] = cconj(acc);
+        }
+    }
+  QK_PAR_END
+
+  qk_jacobi<G>(c, R, C);
+
+  QK_PAR_BEGIN(tid)
+    for (int j = tid; j < C; j += G) {
+      double s = 0.0;
+      const c128* w = W + (size_t)j * ldw;
+      for (int row = 0; row < R; ++row) s += w[row].x * w[row].x + w[row].y * w[row].y;
+      c.nrm2[j] = s;
+    }
+  QK_PAR_END
+  QK_PAR_BEGIN(tid)
+    const double dead = c.P->floor_rel * c.sh->total;
+    for (int j = tid; j < C; j += G) {
+      const double v = c.nrm2[j];
+      int rk = 0;
+      for (int i = 0; i < C; ++i) {
+        const double u = c.nrm2[i];
+        rk += (u > v) || (u == v && i < j);
+      }
+      c.order[rk] = j;
+      const double sg = sqrt(v);
+      c.diag[rk] = cmake(sg, (sg > 0.0 && (v > dead || rk == 0)) ? 1.0 / sg : 0.0);
+    }
+  QK_PAR_END
+  QK_PAR_BEGIN(tid)
+    if (tid == 0) qk_truncate(c, C, c.P->cap[k + 1]);
+  QK_PAR_END
+  const int keep = c.sh->keep;
+  const double renorm = c.sh->renorm;
+
+  // The kept columns stay where they are (addressed through order[]); staging goes behind W when it fits,
+  // else the kept columns are first copied out compactly.  keep * (R + C) <= rmax^2 always holds.
+  const bool fits = (size_t)R * C + (size_t)keep * C <= (size_t)c.P->rmax * c.P->rmax;
+  if (!fits) {
+    // compact copy of the kept columns through registers would break the phase rules; use the swap list
+    QK_PAR_BEGIN(tid)
+      if (tid == 0) {
+        int* pos = (int*)c.scr;
+        int* at = pos + C;
+        for (int j = 0; j < C; ++j) { pos[j] = j; at[j] = j; }
+        for (int t = 0; t < keep; ++t) {
+          const int j = c.order[t], p = pos[j];
+          c.swp[t] = p;
+          if (p != t) { const int jj = at[t]; at[p] = jj; pos[jj] = p; at[t] = j; pos[j] = t; }
+        }
+      }
+    QK_PAR_END
+    QK_PAR_BEGIN(tid)
+      for (int row = tid; row < R; row += G)
+        for (int t = 0; t < keep; ++t) {
+          const int p = c.swp[t];
+          if (p != t) {
+            const c128 x = W[row + (size_t)t * ldw];
+            W[row + (size_t)t * ldw] = W[row + (size_t)p * ldw];
+            W[row + (size_t)p * ldw] = x;
+          }
+        }
+    QK_PAR_END
+  }
+  const bool use_order = fits;
+  c128* S = W + (size_t)R * (fits ? C : keep);    // staging area 1: keep x C entries
+
+  if (transposed) {
+    // W[(R,c), t] = sigma_t * (t-th right singular vector of theta): B'_{k+1} = conj(W)^T / sigma; B'_k = C W / sigma
+    qk_half_left<G>(c, A, B, ca, cb, cc, keep, W, ldw, use_order, false, true, S);
+    QK_PAR_BEGIN(tid)
+      for (int idx = tid; idx < keep * n2; idx += G) {
+        const int t = idx / n2, col = idx - t * n2;
+        B[idx] = cscale(cconj(W[col + (size_t)(use_order ? c.order[t] : t) * ldw]), c.diag[t].y);
+      }
+      for (int idx = tid; idx < m * keep; idx += G) A[idx] = S[idx];
+      for (int t = tid; t < keep; t += G) lamM[t] = c.diag[t].x * renorm;
+      if (tid == 0) c.chi[k + 1] = keep;
+    QK_PAR_END
+  } else {
+    // W[(a,L), t] = sigma_t u_t: V^dag = S^-2 W^dag theta (staged in S), then B'_k = C V (staged over W's head)
+    qk_half_right<G>(c, A, lamL, B, ca, cb, cc, keep, W, ldw, use_order, S);
+    c128* S2 = W;   // m x keep <= R x keep entries: the kept columns of W are dead now
+    qk_half_left<G>(c, A, B, ca, cb, cc, keep, S, n2, false, true, false, S2);
+    QK_PAR_BEGIN(tid)
+      for (int idx = tid; idx < keep * n2; idx += G) B[idx] = S[idx];
+      for (int idx = tid; idx < m * keep; idx += G) A[idx] = S2[idx];
+      for (int t = tid; t < keep; t += G) lamM[t] = c.diag[t].x * renorm;
+      if (tid == 0) c.chi[k + 1] = keep;
+    QK_PAR_END
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Householder QR of W (R x C, column-major ld = R): reflectors H_j = I - 2 u_j u_j^dag with u_j stored
 // in column j (rows j..R-1), R factor in the strict upper triangle + c.diag.  Q (R x kk) -> Qm.
 // ------------------------------------------------------------------------------------------------
@@ -961,6 +1225,69 @@ QK_DEV void qk_sim_datapoint(SimCtx& c, int dp) {
       QkStat st;
       st.fidelity = c.sh->fidelity; st.trunc_weight = c.sh->trunc_weight;
       st.flags = c.sh->flags; st.sweeps = c.sh->sweeps; st.max_chi = c.sh->max_chi; st.pad = 0;
+      P->stats[dp] = st;
+    }
+  QK_PAR_END
+}
+
+// ------------------------------------------------------------------------------------------------
+// whole circuit for datapoint dp in B form.  `ncta` cooperating groups (the CTAs of a thread-block cluster on
+// the device, 1 in the host emulation) share the datapoint: the items of one level are dealt round-robin,
+// QK_GROUP_SYNC() separates levels.  chi and the bond weights live in global memory so that every group
+// sees the others' updates after the barrier.
+// ------------------------------------------------------------------------------------------------
+#ifndef QK_GROUP_SYNC
+#define QK_GROUP_SYNC() ((void)0)
+#endif
+template <int G>
+QK_DEV void qk_sim_datapoint_b(SimCtx& c, int dp, int cta, int ncta, QkStat* part /* [ncta] partial stats of dp */) {
+  const SimParams* P = c.P;
+  const int n = P->n;
+  c.state = P->store + (size_t)dp * P->state_stride;
+  c.lam = P->lam + (size_t)dp * (n + 1) * P->lam_ld;
+  c.chi = P->chi + (size_t)dp * (n + 1);
+  QK_PAR_BEGIN(tid)
+    for (int s = cta * G + tid; s < n; s += G * ncta) {   // |0...0>
+      c128* A = qk_site(c, s);
+      A[0] = cmake(1, 0);
+      A[1] = cmake(0, 0);
+    }
+    for (int b = cta * G + tid; b <= n; b += G * ncta) { c.chi[b] = 1; c.lam[(size_t)b * P->lam_ld] = 1.0; }
+    for (int i = tid; i < n; i += G) c.x[i] = P->X[(size_t)dp * P->ldx + i];
+    if (tid == 0) {
+      c.sh->flags = 0; c.sh->sweeps = 0; c.sh->max_chi = 1;
+      c.sh->fidelity = 1.0; c.sh->trunc_weight = 0.0; c.sh->rotated = 0;
+    }
+  QK_PAR_END
+  QK_GROUP_SYNC();
+  for (int lv = 0; lv < P->n_levels; ++lv) {
+    int item = -1;
+    for (int o = P->level_start[lv]; o < P->level_start[lv + 1]; ++o) {
+      const QkOp op = P->ops[o];
+      if (!(op.pad & QK_OPF_ACC)) ++item;           // a fused group (CONT ... last) is one item
+      if (item % ncta != cta) continue;
+      if (op.kind <= QK_OP_RX) qk_op_1q<G>(c, op);
+      else qk_op_2q_b<G>(c, op);
+    }
+    QK_GROUP_SYNC();
+  }
+  QK_PAR_BEGIN(tid)
+    if (tid == 0) {
+      QkStat st;
+      st.fidelity = c.sh->fidelity; st.trunc_weight = c.sh->trunc_weight;
+      st.flags = c.sh->flags; st.sweeps = c.sh->sweeps; st.max_chi = c.sh->max_chi; st.pad = 0;
+      part[cta] = st;
+    }
+  QK_PAR_END
+  QK_GROUP_SYNC();
+  QK_PAR_BEGIN(tid)
+    if (cta == 0 && tid == 0) {
+      QkStat st = part[0];
+      for (int i = 1; i < ncta; ++i) {
+        st.fidelity *= part[i].fidelity; st.trunc_weight += part[i].trunc_weight;
+        st.flags |= part[i].flags; st.sweeps += part[i].sweeps;
+        if (part[i].max_chi > st.max_chi) st.max_chi = part[i].max_chi;
+      }
       P->stats[dp] = st;
     }
   QK_PAR_END

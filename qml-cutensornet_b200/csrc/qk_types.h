@@ -97,4 +97,10 @@ struct SimParams {
   int early_exit;            // stop a datapoint at its first bond-cap hit (state then invalid, flag set)
   double floor_rel;          // Jacobi: columns below floor_rel * total weight are treated as numerically zero
   double abs_rel;            // Jacobi: no rotation when |x^dag y| <= abs_rel * total weight
+  // B-form (QK_PLAN_PARALLEL): Schmidt values of every bond, op levels
+  int parallel;              // 1: ops are levelised; state is kept right-canonical with explicit bond weights
+  double* lam;               // [N][(n+1)][lam_ld] Schmidt values per bond (global)
+  int lam_ld;                // = max bond cap
+  const int32_t* level_start;  // [n_levels+1] first op of every level
+  int n_levels;
 };

@@ -25,6 +25,7 @@ QK_ERR_LIMIT = -3
 QK_PLAN_LITERAL_ORDER = 1
 QK_PLAN_EARLY_EXIT = 2
 QK_PLAN_NO_FUSION = 4
+QK_PLAN_PARALLEL = 8
 CHI_LIMIT = 32          # shared-memory-resident stage-1 kernel
 DMMA_D_LIMIT = 16       # register-resident tensor-core overlap kernel
 
@@ -139,6 +140,8 @@ class Plan:
             flags |= QK_PLAN_LITERAL_ORDER
         if os.environ.get("QK_SCHEDULE", "") == "nofuse":
             flags |= QK_PLAN_NO_FUSION
+        if os.environ.get("QK_SCHEDULE", "") == "parallel":
+            flags |= QK_PLAN_PARALLEL
         _check(lib().qk_plan_create_gates(int(n_qubits), carr, len(gates), int(trunc_mode),
                                           ctypes.c_double(trunc_error), int(chi_cap), int(flags),
                                           ctypes.byref(self._h)))

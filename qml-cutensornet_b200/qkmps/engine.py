@@ -24,6 +24,7 @@ import os
 from . import (CHI_LIMIT, DMMA_D_LIMIT, QK_FLAG_CAP_HIT, QK_FLAG_NO_CONVERGE, Batch, Plan, QkError, frag_stride,
                gram_frags, gram_lane, pad_dims, simulate_dev)
 
+PARALLEL_MAX_LOCAL = 150   # datapoints per GPU up to which stage 1 uses one CTA cluster per datapoint
 LANE_CHI_LIMIT = 4   # at or below this bond dimension stage 2 runs one lane per pair on the FP64 CUDA cores
 
 
@@ -157,8 +158,15 @@ def _simulate_shard(plan_factory, X_shard, device, chi_cap, comm, n_qubits, esca
         raise QkError(-3, f"bond dimension cap {chi_cap} above the shared-memory-resident limit (chi <= {CHI_LIMIT})")
     stream = torch.cuda.current_stream().cuda_stream
 
+    # Small shards (the multi-GPU regime: 125 datapoints per GPU at 8 GPUs) are bound by the latency of ONE
+    # datapoint's op chain.  They run in B form with a cluster of CTAs per datapoint (QK_PLAN_PARALLEL): the
+    # dependency depth of the circuit replaces its op count.  Large shards keep the sequential fused schedule,
+    # which does 25 % fewer and smaller SVDs and is throughput-bound anyway.
+    env = os.environ.get("QK_SCHEDULE", "")
+    parallel = (env == "parallel") or (env == "" and comm.Get_size() > 1 and 0 < n_local <= PARALLEL_MAX_LOCAL)
+
     def run(cap, idx, early):
-        plan = plan_factory(cap, early)
+        plan = plan_factory(cap, early, True) if parallel else plan_factory(cap, early)
         sub = xt if len(idx) == n_local and np.array_equal(idx, np.arange(n_local)) else xt[torch.from_numpy(idx).to(xt.device)]
         batch = simulate_dev(plan, sub.data_ptr(), int(sub.shape[0]), int(sub.shape[1]), device=device, stream=stream)
         info = batch.info()

@@ -17,7 +17,12 @@ template <int G>
 static void run_group(const SimParams& P, unsigned char* smem, int dp) {
   SimCtx c;
   qk_sim_carve(c, &P, smem, G);
-  qk_sim_datapoint<G>(c, dp);
+  if (P.parallel) {
+    QkStat part;
+    qk_sim_datapoint_b<G>(c, dp, 0, 1, &part);
+  } else {
+    qk_sim_datapoint<G>(c, dp);
+  }
 }
 
 extern "C" {
@@ -48,6 +53,14 @@ long long qk_emu_simulate(int n, const qk_gate* gates, int n_gates, int trunc_mo
   P.tol = getenv("QK_EMU_TOL") ? atof(getenv("QK_EMU_TOL")) : 1e-15; P.max_sweeps = getenv("QK_EMU_SWEEPS") ? atoi(getenv("QK_EMU_SWEEPS")) : 60; P.rmax = plan.rmax; P.wr = plan.rmax * plan.rmax; P.trace = nullptr; P.early_exit = (flags & 2) ? 1 : 0;
   P.floor_rel = getenv("QK_EMU_FLOOR") ? atof(getenv("QK_EMU_FLOOR")) : 1e-28;
   P.abs_rel = getenv("QK_EMU_ABS") ? atof(getenv("QK_EMU_ABS")) : 0.0;
+  std::vector<double> lam;
+  P.parallel = plan.parallel; P.lam = nullptr; P.lam_ld = plan.rmax / 2; P.level_start = nullptr; P.n_levels = 0;
+  if (plan.parallel) {
+    lam.assign((size_t)N * (n + 1) * P.lam_ld, 0.0);
+    P.lam = lam.data();
+    P.level_start = plan.level_start.data();
+    P.n_levels = (int)plan.level_start.size() - 1;
+  }
   size_t bytes = qk_sim_smem_bytes(n, plan.rmax, G);
   unsigned char* smem = (unsigned char*)aligned_alloc(64, (bytes + 63) & ~(size_t)63);
   for (int dp = 0; dp < N; ++dp) {

@@ -385,3 +385,35 @@ def test_low_chi_lane_kernel(qk, cuda_device, monkeypatch, n, r, g, d, nx, ny):
     assert build_kernel_matrix.last_profile["gram_kernel"] == "qk_gram_dmma_kernel"
     Kt2 = build_kernel_matrix(SingleComm(), ans, X, Y, truncation_error=1e-16)
     assert np.abs(K - K2).max() < 1e-12 and np.abs(Kt - Kt2).max() < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,r,g,d,N", [(12, 2, 0.8, 2, 19), (16, 3, 0.4, 1, 9), (14, 2, 1.0, 2, 6)])
+def test_parallel_b_form_schedule(qk, cuda_device, monkeypatch, n, r, g, d, N):
+    """QK_PLAN_PARALLEL: one CTA cluster per datapoint, B form, ops levelised (the path small multi-GPU shards
+    take).  Gram against the exact statevector and against the sequential schedule; identical results for
+    cluster sizes 1 and 6 (the levels only change who executes an op, not its arithmetic)."""
+    from gpu_backend.kernel_state_ansatz import build_kernel_matrix
+    from qkmps.engine import SingleComm
+    emap = oracle.entanglement_graph(n, d)
+    X = oracle.synthetic_features(N, n, 7)
+    ans = _ansatz(n, r, g, d)
+    Kseq = build_kernel_matrix(SingleComm(), ans, X, truncation_error=1e-16)
+    assert build_kernel_matrix.last_profile["plan"].n_moves == 0
+    monkeypatch.setenv("QK_SCHEDULE", "parallel")
+    Kpar = build_kernel_matrix(SingleComm(), ans, X, truncation_error=1e-16)
+    ops_par = build_kernel_matrix.last_profile["plan"].n_ops
+    monkeypatch.setenv("QK_SIM_CLUSTER", "1")
+    Kpar1 = build_kernel_matrix(SingleComm(), ans, X, truncation_error=1e-16)
+    Ksv = oracle.statevector_gram(n, r, g, emap, X)
+    assert ops_par > 0
+    assert np.abs(Kpar - Ksv).max() < TOL and np.abs(Kseq - Ksv).max() < TOL
+    assert np.abs(Kpar - Kseq).max() < TOL
+    assert np.array_equal(Kpar, Kpar1)
+    batch = qk.simulate(_plan(qk, ans, 0, 16, flags=qk.QK_PLAN_PARALLEL), X)     # ITensors rule through the C ABI
+    info = batch.info()
+    assert not np.any(info["flags"])
+    ref = simulate_batch(n, r, g, emap, X, mode="itensors")
+    assert np.array_equal(info["chi"], np.array([[1] + m.bond_dims() + [1] for m in ref]))
+    K, _ = batch.gram_store()
+    assert np.abs(K - Ksv).max() < TOL

@@ -134,3 +134,37 @@ def test_emu_early_exit(emu):
         assert np.array_equal(chi_ee[i], chi_full[i])
         a, b = TensorsMPS(s_ee[i]), TensorsMPS(s_full[i])
         assert abs(abs(mps_inner(a, b)) ** 2 - 1) < 1e-12
+
+
+@pytest.mark.parametrize("n,r,g,d,cap,mode", [(8, 2, 0.7, 2, 16, 0), (10, 2, 1.0, 2, 16, 1), (12, 3, 0.5, 1, 8, 0),
+                                              (11, 2, 0.9, 3, 32, 1), (24, 2, 0.1, 2, 16, 0)])
+def test_emu_parallel_b_form(emu, n, r, g, d, cap, mode):
+    """QK_PLAN_PARALLEL (flags = 8): B form with explicit Schmidt values, no gauge moves, ops levelised by the
+    sites they touch.  Same states as the oracle (fidelity, Gram, statevector) and -- the Schmidt spectra being
+    the same -- the same bond dimensions under the ITensors rule; every tensor stays right-orthonormal."""
+    N = 4
+    X = oracle.synthetic_features(N, n, 2)
+    emap = oracle.entanglement_graph(n, d)
+    gates = oracle.ansatz_gate_list(n, r, g, emap)
+    states, chi, stats, (n_ops, n_moves) = emu_simulate(emu, n, gates, X, trunc_mode=mode, chi_cap=cap, flags=8)
+    assert n_moves == 0 and not stats[:, 2].any()
+    ref = simulate_batch(n, r, g, emap, X, mode="itensors" if mode == 0 else "pytket")
+    ms = [TensorsMPS(s) for s in states]
+    for i in range(N):
+        assert abs(abs(mps_inner(ms[i], ref[i])) ** 2 - 1) < 1e-10
+    # a different (equally valid) sequence of 1e-16 truncations: Gram entries agree to the 1e-8 of the spec
+    # (observed 1e-13 .. 1.5e-9), not to the 1e-11 of the literal sequential order
+    assert np.abs(gram_from_mps(ms) - gram_from_mps(ref)).max() < 1e-8
+    if n <= 12:
+        assert np.abs(gram_from_mps(ms) - oracle.statevector_gram(n, r, g, emap, X)).max() < 1e-8
+    if mode == 0:
+        assert np.array_equal(chi, np.array([[1] + m.bond_dims() + [1] for m in ref]))
+    # right-orthonormal site tensors (B form), except the first (norm).  A row that belongs to a Schmidt value
+    # near the cutoff (weight ~1e-16) loses part of its norm when a neighbouring bond is truncated by a similar
+    # weight -- inherent to TEBD-style updates and invisible in the state (the row is weighted by that value) --
+    # so the bound is loose; rows of O(1) weight are orthonormal to 1e-14.
+    for s in states:
+        for A in s[1:]:
+            M = A.reshape(A.shape[0], -1)
+            dev = np.abs(M @ M.conj().T - np.eye(M.shape[0]))
+            assert dev.max() < 1e-3 and dev[0, 0] < 1e-12
