@@ -508,7 +508,9 @@ int qk_gram_frags(int device, void* stream_v, int n_qubits, const int32_t* Dx, c
     int64_t per_state = Ltmp.stride_bytes;
     qk_frag_layout(n_qubits, Dy, &Ltmp, nullptr);
     per_state = std::max<int64_t>(per_state, Ltmp.stride_bytes);
-    S = (int)std::max<int64_t>(8, ((int64_t)32 << 20) / std::max<int64_t>(per_state, 1));
+    int64_t budget = (int64_t)32 << 20;    // bytes of kets (and as many of bras) per supertile
+    if (const char* ev = getenv("QK_GRAM_SUPERTILE_MB")) { const int v = atoi(ev); if (v > 0) budget = (int64_t)v << 20; }
+    S = (int)std::max<int64_t>(8, budget / std::max<int64_t>(per_state, 1));
     S = std::max(8, S / 8 * 8);
   }
   std::vector<int4> cta;

@@ -61,7 +61,13 @@ def row_tiles(n_rows: int, n_cols: int, symmetric: bool, n_ranks: int, rank: int
         if owner != rank:
             continue
         r0, r1 = b * row_block, min((b + 1) * row_block, n_rows)
-        tiles.append([r0, r1, 0, min(r1, n_cols) if symmetric else n_cols])
+        c1 = min(r1, n_cols) if symmetric else n_cols
+        if tiles and tiles[-1][1] == r0:
+            # contiguous with the previous block of this rank (always, on one rank): one larger tile, so that the
+            # L2 supertiles of qk_gram_frags can block over rows as well as columns
+            tiles[-1][1], tiles[-1][3] = r1, c1
+        else:
+            tiles.append([r0, r1, 0, c1])
     return tiles
 
 
