@@ -21,7 +21,7 @@ import numpy as np
 
 import os
 
-from . import (CHI_LIMIT, DMMA_D_LIMIT, QK_FLAG_CAP_HIT, QK_FLAG_NO_CONVERGE, Batch, Plan, QkError, frag_stride,
+from . import (CHI_LIMIT, DMMA_D_LIMIT, QK_FLAG_CAP_HIT, QK_FLAG_NO_CONVERGE, QkError, frag_stride,
                gram_frags, gram_lane, pad_dims, simulate_dev)
 
 PARALLEL_MAX_LOCAL = 150   # datapoints per GPU up to which stage 1 uses one CTA cluster per datapoint
