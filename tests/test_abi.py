@@ -104,32 +104,39 @@ def test_plan_counts_and_schedule_invariants(qk, n, r, d, n2q):
     _replay(plan3)
 
 
-@pytest.mark.parametrize("n,r,d,n2q,depth", [(10, 2, 1, 18, 4), (50, 2, 2, 386, 28), (100, 2, 2, 786, 28), (165, 2, 1, 328, 4)])
-def test_parallel_plan_levels(qk, n, r, d, n2q, depth):
-    """QK_PLAN_PARALLEL: no gauge moves, the literal circuit's ops grouped into levels (op.dir = level) such that
-    the ops of a level touch disjoint sites, every site sees its ops in circuit order, and the number of levels
-    that contain 2-qubit ops is the dependency depth of the circuit (independent of the number of qubits)."""
-    plan, gates = _plan(qk, n, r, 0.5, d, flags=qk.QK_PLAN_PARALLEL)
-    info = plan.info()
-    assert info.n_moves == 0 and info.n_ops_2q == n2q and info.n_ops_1q == n * (r + 1)
-    ops = plan.ops()
-    levels = [o[4] for o in ops]
-    assert levels == sorted(levels)                      # ops are emitted level by level
-    per_site = {s: [] for s in range(n)}
-    two_q_levels = set()
-    for lv in sorted(set(levels)):
-        used = set()
-        for k, s, fa, fb, l, *_ in ops:
-            if l != lv:
-                continue
-            sites = (s, s + 1) if 3 <= k <= 5 else (s,)
-            assert not (used & set(sites)), "two ops of one level share a site"
-            used |= set(sites)
-            for q in sites:
-                per_site[q].append((k, s, fa, fb))
-            if 3 <= k <= 5:
-                two_q_levels.add(lv)
-    assert len(two_q_levels) == depth
+@pytest.mark.parametrize("n,r,d,n2q,depth,n2q_paired,depth_paired",
+                         [(10, 2, 1, 18, 4, 18, 4), (50, 2, 2, 386, 28, 290, 14), (100, 2, 2, 786, 28, 590, 14),
+                          (165, 2, 1, 328, 4, 328, 4)])
+def test_parallel_plan_levels(qk, n, r, d, n2q, depth, n2q_paired, depth_paired):
+    """QK_PLAN_PARALLEL: no gauge moves, ops grouped into levels (op.dir = level) such that the ops of a level
+    touch disjoint sites; the number of levels that contain 2-qubit ops is the dependency depth of the circuit
+    (independent of the number of qubits).  With QK_PLAN_LITERAL_ORDER every site sees its ops in circuit order;
+    by default interleaved distance-2 pairs share one swap (same interactions, fewer ops, half the depth)."""
+    def check(plan, want_2q, want_depth):
+        info = plan.info()
+        assert info.n_moves == 0 and info.n_ops_2q == want_2q and info.n_ops_1q == n * (r + 1)
+        ops = plan.ops()
+        levels = [o[4] for o in ops]
+        assert levels == sorted(levels)                      # ops are emitted level by level
+        per_site = {s: [] for s in range(n)}
+        two_q_levels = set()
+        for lv in sorted(set(levels)):
+            used = set()
+            for k, s, fa, fb, l, *_ in ops:
+                if l != lv:
+                    continue
+                sites = (s, s + 1) if 3 <= k <= 5 else (s,)
+                assert not (used & set(sites)), "two ops of one level share a site"
+                used |= set(sites)
+                for q in sites:
+                    per_site[q].append((k, s, fa, fb))
+                if 3 <= k <= 5:
+                    two_q_levels.add(lv)
+        assert len(two_q_levels) == want_depth
+        return ops, per_site
+
+    plan, gates = _plan(qk, n, r, 0.5, d, flags=qk.QK_PLAN_PARALLEL | qk.QK_PLAN_LITERAL_ORDER)
+    ops_lit, per_site = check(plan, n2q, depth)
     ref_site = {s: [] for s in range(n)}                 # the circuit's own order, per site
     for nm, q, prm in gates:
         k = qk.GATE_KIND[nm]
@@ -138,6 +145,10 @@ def test_parallel_plan_levels(qk, n, r, d, n2q, depth):
         for site in q:
             ref_site[site].append((k, q[0], fa, fb))
     assert per_site == ref_site
+    plan2, _ = _plan(qk, n, r, 0.5, d, flags=qk.QK_PLAN_PARALLEL)
+    ops_pair, _ = check(plan2, n2q_paired, depth_paired)
+    xx = lambda ops: sorted((o[2], o[3]) for o in ops if o[0] == 3)   # noqa: E731
+    assert xx(ops_pair) == xx(ops_lit)                   # every interaction still there exactly once
 
 
 def test_plan_from_ansatz_equals_plan_from_gates(qk):
