@@ -402,7 +402,8 @@ def run_ours(args):
                    "l2": f"flushed with a {L2_FLUSH_BYTES >> 20} MiB write between timed iterations; packed states "
                          f"({prof['frag_bytes_per_state'][0] * N >> 20} MiB) exceed the 126 MB L2",
                    "parallelism": f"datapoints sharded over {world} GPU(s); all-gather of packed states; row blocks of K "
-                                  "dealt to ranks"},
+                                  "dealt to ranks",
+                   "stage1_schedule": prof.get("stage1_schedule", ""), "stage2_kernel": prof.get("gram_kernel", "")},
         "circuits_per_s": N / (ms_per_step * 1e-3),
         "stage_ms": {"simulate": sim_mean, "gram": gram_mean, "other": ms_per_step - sim_mean - gram_mean},
         "roofline": roofline, "stages": {"simulate": stage1, "gram": stage2},

@@ -101,6 +101,7 @@ class ShardStates:
         self.sim_ms = 0.0
         self.launches = 0
         self.cap = 1
+        self.schedule = ""
 
     def add(self, batch, info, ok_in_batch, shard_pos):
         self.parts.append((batch, info, np.asarray(ok_in_batch, dtype=np.int64), np.asarray(shard_pos, dtype=np.int64)))
@@ -167,9 +168,11 @@ def _simulate_shard(plan_factory, X_shard, device, chi_cap, comm, n_qubits, esca
     # Small shards (the multi-GPU regime: 125 datapoints per GPU at 8 GPUs) are bound by the latency of ONE
     # datapoint's op chain.  They run in B form with a cluster of CTAs per datapoint (QK_PLAN_PARALLEL): the
     # dependency depth of the circuit replaces its op count.  Large shards keep the sequential fused schedule,
-    # which does 25 % fewer and smaller SVDs and is throughput-bound anyway.
+    # which is throughput-bound anyway (1000 CTAs per 125 datapoints already saturate the SMs).
     env = os.environ.get("QK_SCHEDULE", "")
     parallel = (env == "parallel") or (env == "" and comm.Get_size() > 1 and 0 < n_local <= PARALLEL_MAX_LOCAL)
+
+    states.schedule = "parallel (B form, one CTA cluster per datapoint)" if parallel else "sequential (one CTA per datapoint)"
 
     def run(cap, idx, early):
         plan = plan_factory(cap, early, True) if parallel else plan_factory(cap, early)
@@ -238,6 +241,7 @@ def build_gram(comm, plan_factory, n_qubits, X, Y=None, chi_cap=16, device=None,
     prof["chi_cap"] = max(sx.cap, sy.cap if sy is not None else 1)
     prof["info_x"], prof["info_y"] = info_x, info_y
     prof["plan"] = sx.plan.info()
+    prof["stage1_schedule"] = sx.schedule
     prof["plan_obj"] = sx.plan
     prof["shard"] = (lo, hi)
 
