@@ -2,18 +2,21 @@
 """bench.py -- one JSON line for the quantum-kernel hot path on N B200s.
 
 A "step" is one pass of the hot path over one batch: simulate every datapoint's ansatz circuit as
-an MPS (stage 1), pack + exchange the states, and build the full train Gram matrix (stage 2).
-Workload = BASELINE.json configs[2] (the config the 1/2/4/8-GPU metric is quoted on; it fits one
+an MPS (stage 1), exchange the states, and build the Gram matrix (stage 2).
+Default workload = BASELINE.json configs[2] (the config the 1/2/4/8-GPU metric is quoted on; it fits one
 GPU): 50 qubits, 2 layers, distance 2, 1000 synthetic points, gamma = 1.0 (maximal bond dimension).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c5|c4|...]
 
-`value`   Gram entries/s (unique entries N(N+1)/2 per step), inputs resident in HBM, CUDA events.
+`value`   Gram entries/s (unique entries per step), inputs resident in HBM, CUDA events, max over ranks.
 `e2e`     same metric through the reference-facing entry point gpu_backend.build_kernel_matrix with
           HOST numpy buffers (H2D of X and D2H of K inside the timed region).
-`--impl reference` times the CPU restatement of the reference (oracle/, ITensors semantics) on the
-          host cores; the reference's own backends (Julia/ITensors, pytket-cutensornet) do not
-          install offline.
+`parity`  rank 0 compares the Gram matrix the timed path produced with (a) the CPU oracle on a sample of states
+          (all pairs among them) and (b) the CUDA-core cross-check kernel on a slab of rows; the run exits
+          non-zero when max_abs_err exceeds the 1e-8 of BASELINE.json.  Printed at every N.
+`--impl reference` times the CPU restatement of the reference (oracle/) on the host cores with the same
+          truncation rule as the GPU arm; the reference's own backends (Julia/ITensors, pytket-cutensornet)
+          do not install offline.
 """
 import argparse
 import json
@@ -31,13 +34,41 @@ sys.path.insert(0, str(ROOT / "qml-cutensornet_b200"))
 sys.path.insert(0, str(ROOT))
 
 WORKLOADS = {
-    # name: (n_qubits, reps, distance, gamma, n_points)
-    "c3": (50, 2, 2, 1.0, 1000),
-    "c3_g0.1": (50, 2, 2, 0.1, 1000),
-    "c2": (20, 2, 1, 0.5, 200),
-    "c1": (10, 2, 1, 0.5, 40),
+    # name: (n_qubits, reps, distance, gamma, n_train, n_test)   n_test = 0: symmetric train Gram
+    "c3": (50, 2, 2, 1.0, 1000, 0),
+    "c3_g0.1": (50, 2, 2, 0.1, 1000, 0),
+    "c2": (20, 2, 1, 0.5, 200, 0),
+    "c1": (10, 2, 1, 0.5, 40, 0),
+    "c5": (100, 2, 2, 1.0, 1000, 1000),        # BASELINE configs[4]: train x test rectangular Gram
+    "c5_g0.1": (100, 2, 2, 0.1, 1000, 1000),
+    "c4": (165, 4, 4, 0.5, 64, 0),             # BASELINE configs[3]: high bond dimension (chi ~ 100)
+    "c4_g0.1": (165, 4, 4, 0.1, 256, 0),
 }
 L2_FLUSH_BYTES = 256 << 20
+TRUNC_ERROR = 1e-16
+PARITY_TOL = 1e-8       # BASELINE.json north_star: Gram entries within 1e-8 absolute
+
+
+def n_entries(N, M):
+    return N * (N + 1) // 2 if M == 0 else N * M
+
+
+def workload_config(name):
+    """`config` of the JSON line -- identical in both arms (the driver compares them)."""
+    n, r, d, g, N, M = WORKLOADS[name]
+    shape = f"{N} points, full train Gram ({n_entries(N, M)} unique entries)" if M == 0 else \
+        f"{N} train x {M} test points, rectangular Gram ({n_entries(N, M)} entries)"
+    return {"workload": f"{name}: {n} qubits, {r} layers, distance {d}, gamma {g}, {shape}",
+            "truncation_error": TRUNC_ERROR, "trunc_rule": "pytket (kept weight fraction >= 1 - truncation_error)",
+            "l2": f"GPU arm: L2 flushed with a {L2_FLUSH_BYTES >> 20} MiB write between timed iterations"}
+
+
+def workload_inputs(name):
+    from qkmps.synth import synthetic_features      # product-side generator (numpy only; same as oracle.synth)
+    n, r, d, g, N, M = WORKLOADS[name]
+    X = synthetic_features(N, n, 0)
+    Y = synthetic_features(M, n, 1) if M else None
+    return X, Y
 
 
 # --------------------------------------------------------------------------------------- CPU arm
@@ -50,11 +81,11 @@ def _cpu_worker_init():
 
 
 def _cpu_sim_one(args):
-    n, gates, x, cutoff = args
+    n, gates, x, cutoff, mode = args
     from oracle.ansatz import bind_gate_list
     from oracle.mps_ref import simulate_mps
     t0 = time.perf_counter()
-    m = simulate_mps(n, bind_gate_list(gates, x), cutoff, "itensors")
+    m = simulate_mps(n, bind_gate_list(gates, x), cutoff, mode)
     return time.perf_counter() - t0, m.tensors
 
 
@@ -73,55 +104,142 @@ def _cpu_inner_chunk(pairs):
     t0 = time.perf_counter()
     for (i, j) in pairs:
         out.append(abs(inner_prepared(prep[i][1], prep[j][0], prep[j][2])) ** 2)
-    return time.perf_counter() - t0, len(pairs)
+    return time.perf_counter() - t0, len(pairs), out
 
 
-def cpu_reference_sample(workload, budget_s=14.0, cores=None):
-    """Time the oracle port (ITensors semantics) on the host cores on a bounded sample of the workload
-    and extrapolate to the whole job: est = N*t_circ/P + pairs*t_inner/P."""
+def cpu_reference_sample(workload, budget_s=14.0, cores=None, mode="pytket"):
+    """Time the oracle port on the host cores on a bounded sample of the workload and extrapolate to the
+    whole job the way the reference's CPU backend distributes it (circuits and pairs dealt to P processes):
+    est = n_circuits * t_circ / P + n_pairs * t_inner / P."""
     import multiprocessing as mp
     from oracle.ansatz import ansatz_gate_list, entanglement_graph
-    from oracle.synth import synthetic_features
-    n, r, d, g, N = WORKLOADS[workload]
+    n, r, d, g, N, M = WORKLOADS[workload]
     P = cores or len(os.sched_getaffinity(0))
     gates = ansatz_gate_list(n, r, g, entanglement_graph(n, d))
-    X = synthetic_features(N, n, 0)
+    X, Y = workload_inputs(workload)
     t0 = time.perf_counter()
-    tc, _ = _cpu_sim_one((n, gates, X[0], 1e-16))
+    tc, _ = _cpu_sim_one((n, gates, X[0], TRUNC_ERROR, mode))
     n_circ = int(min(N, max(P, (0.6 * budget_s) * P / max(tc, 1e-4))))
+    n_circ = max(n_circ, min(N, 2))
     global _G_TENSORS
     ctx = mp.get_context("fork")
     with ctx.Pool(P, initializer=_cpu_worker_init) as pool:
         w0 = time.perf_counter()
-        res = pool.map(_cpu_sim_one, [(n, gates, X[i], 1e-16) for i in range(n_circ)], chunksize=max(1, n_circ // (4 * P)))
+        res = pool.map(_cpu_sim_one, [(n, gates, X[i], TRUNC_ERROR, mode) for i in range(n_circ)],
+                       chunksize=max(1, n_circ // (4 * P)))
         wall_c = time.perf_counter() - w0
     t_circ = [t for t, _ in res]
     _G_TENSORS = [t for _, t in res]
-    # inner products on the simulated sample
+    # inner products among the simulated sample: distinct pairs, drawn without replacement
     rng = np.random.default_rng(1)
-    tp, _ = _cpu_inner_chunk([(0, min(1, n_circ - 1))] * 8)
+    tp, _, _ = _cpu_inner_chunk([(0, min(1, n_circ - 1))] * 8)
     tp /= 8
-    n_pairs = int(max(P, (0.3 * budget_s) * P / max(tp, 1e-6)))
-    idx = rng.integers(0, n_circ, size=(n_pairs, 2))
+    avail = n_circ * (n_circ + 1) // 2
+    n_pairs = int(min(avail, max(P, (0.3 * budget_s) * P / max(tp, 1e-6))))
+    flat = rng.choice(avail, size=n_pairs, replace=False)
+    ii = (np.floor((np.sqrt(8.0 * flat + 1.0) - 1.0) / 2.0)).astype(np.int64)      # row of the lower triangle
+    ii -= (ii * (ii + 1) // 2 > flat)
+    jj = flat - ii * (ii + 1) // 2
+    idx = np.stack([ii, jj], axis=1)
     chunks = [[(int(a), int(b)) for a, b in c] for c in np.array_split(idx, 4 * P) if len(c)]
     with ctx.Pool(P, initializer=_cpu_worker_init) as pool:
         w0 = time.perf_counter()
         res = pool.map(_cpu_inner_chunk, chunks)
         wall_p = time.perf_counter() - w0
     _G_TENSORS = None
-    pairs_total = N * (N + 1) // 2
+    circuits_total = N + M
+    pairs_total = n_entries(N, M)
     per_circ_wall = wall_c / n_circ          # already divided by P through the pool
     per_pair_wall = wall_p / n_pairs
-    est = N * per_circ_wall + pairs_total * per_pair_wall
+    est = circuits_total * per_circ_wall + pairs_total * per_pair_wall
     return {
         "value": pairs_total / est, "unit": "entries/s", "cores": P, "kind": "port",
-        "sample": f"{n_circ} of {N} circuits + {n_pairs} of {pairs_total} inner products on {P} processes "
-                  f"(BLAS 1 thread each), extrapolated to the whole job",
+        "sample": f"{n_circ} of {circuits_total} circuits and {n_pairs} distinct pairs (drawn without replacement among "
+                  f"the sampled circuits) of {pairs_total} inner products, on {P} processes (BLAS 1 thread each); "
+                  f"job time extrapolated as circuits*t_circ/P + pairs*t_inner/P",
         "circuits_per_s": 1.0 / per_circ_wall, "inner_products_per_s": 1.0 / per_pair_wall,
         "median_s_per_circuit_1core": float(np.median(t_circ)),
-        "median_s_per_inner_1core": float(np.median([t / c for t, c in res])),
-        "sample_wall_s": time.perf_counter() - t0,
+        "median_s_per_inner_1core": float(np.median([t / c for t, c, _ in res])),
+        "sample_wall_s": time.perf_counter() - t0, "est_job_s": est, "trunc_rule": mode,
     }
+
+
+# --------------------------------------------------------------------------------------- parity
+def parity_reference(workload, n_states, mode="pytket"):
+    """Oracle side of the parity check (run on rank 0 BEFORE CUDA is initialised: fork pool).  Simulates
+    `n_states` states spread over the whole dataset (so that every rank's shard is represented) with the GPU arm's
+    truncation rule, and all overlaps among them; plus their ITensors-rule bond dimensions."""
+    import multiprocessing as mp
+    from oracle.ansatz import ansatz_gate_list, entanglement_graph
+    n, r, d, g, N, M = WORKLOADS[workload]
+    X, Y = workload_inputs(workload)
+    P = len(os.sched_getaffinity(0))
+    gates = ansatz_gate_list(n, r, g, entanglement_graph(n, d))
+    sx = np.unique(np.linspace(0, N - 1, min(n_states, N)).round().astype(int))
+    sy = np.unique(np.linspace(0, M - 1, min(n_states, M)).round().astype(int)) if M else None
+    jobs = [(n, gates, X[i], TRUNC_ERROR, mode) for i in sx]
+    if M:
+        jobs += [(n, gates, Y[i], TRUNC_ERROR, mode) for i in sy]
+    jobs_it = [(n, gates, X[i], TRUNC_ERROR, "itensors") for i in sx[:8]]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(min(P, len(jobs)), initializer=_cpu_worker_init) as pool:
+        res = pool.map(_cpu_sim_one, jobs + jobs_it)
+    tens = [t for _, t in res[:len(jobs)]]
+    tens_it = [t for _, t in res[len(jobs):]]
+    from oracle.mps_ref import inner_prepared, prepare_for_inner
+    prep = [prepare_for_inner(t) for t in tens]
+    nx = len(sx)
+    if M:
+        ov = np.array([[inner_prepared(prep[nx + a][1], prep[b][0], prep[b][2]) for b in range(nx)] for a in range(len(sy))])
+    else:
+        ov = np.array([[inner_prepared(prep[a][1], prep[b][0], prep[b][2]) for b in range(nx)] for a in range(nx)])
+    chi_it = np.array([[1] + [t.shape[2] for t in ts] for ts in tens_it], dtype=np.int32)
+    return {"sx": sx, "sy": sy, "overlap": ov, "chi_itensors": chi_it, "sx_itensors": sx[:8]}
+
+
+def parity_check(K, ref, workload, qkmps, ans, device, capx, slab_rows=64):
+    """K: the Gram matrix of the timed path (host array on rank 0)."""
+    n, r, d, g, N, M = WORKLOADS[workload]
+    X, Y = workload_inputs(workload)
+    sx, sy = ref["sx"], ref["sy"]
+    Kref = np.abs(ref["overlap"]) ** 2
+    Ks = K[np.ix_(sy if M else sx, sx)]
+    abs_err = float(np.abs(Ks - Kref).max())
+    rel = np.abs(Ks - Kref) / np.maximum(Kref, 1e-300)
+    out = {"max_abs_err": abs_err, "tol_abs": PARITY_TOL, "n_checked": int(Ks.size),
+           "oracle": f"numpy restatement, pytket rule, {len(sx)}{' x ' + str(len(sy)) if M else ''} sampled states "
+                     "(all their pairs)",
+           "max_rel_err_vs_oracle": float(rel.max()), "median_rel_err_vs_oracle": float(np.median(rel)),
+           "min_entry_checked": float(Kref.min())}
+    # ITensors-rule bond dimensions through the C ABI (literal gate order = the oracle's order)
+    gates = ans.ansatz_circ.get_commands()
+    cap = int(max(16, 2 ** int(np.ceil(np.log2(max(ref["chi_itensors"].max(), 1))))))
+    try:
+        plan_it = qkmps.Plan(n, gates, qkmps.QK_TRUNC_ITENSORS, TRUNC_ERROR, cap, qkmps.QK_PLAN_LITERAL_ORDER)
+        b_it = qkmps.simulate(plan_it, X[ref["sx_itensors"]], device=device)
+        out["chi_equal_itensors"] = bool(np.array_equal(b_it.info()["chi"], ref["chi_itensors"]))
+    except Exception as e:   # noqa: BLE001
+        out["chi_equal_itensors"] = f"not checked: {e}"
+    # slab of rows against the CUDA-core cross-check kernel (states re-simulated on this GPU, sequential schedule)
+    try:
+        plan = qkmps.Plan(n, gates, qkmps.QK_TRUNC_PYTKET, TRUNC_ERROR, capx, 0)
+        rows = np.arange(min(slab_rows, M if M else N)) + (100 if (M if M else N) >= 100 + slab_rows else 0)
+        bx = qkmps.simulate(plan, X, device=device)
+        by = qkmps.simulate(plan, (Y if M else X)[rows], device=device)
+        K0, _ = bx.gram_store(by)
+        dk = np.abs(K[rows, :] - K0)
+        out["slab_rows"] = int(len(rows))
+        out["slab_max_abs_err"] = float(dk.max())
+        out["slab_max_rel_err"] = float((dk / np.maximum(K0, 1e-300)).max())
+        out["max_abs_err"] = max(out["max_abs_err"], out["slab_max_abs_err"])
+        out["n_checked"] += int(K0.size)
+    except Exception as e:   # noqa: BLE001
+        out["slab"] = f"not checked: {e}"
+    if M == 0:
+        out["symmetric_exact"] = bool(np.array_equal(K, K.T))
+        out["max_diag_err"] = float(np.abs(np.diag(K) - 1.0).max())
+    out["pass"] = bool(out["max_abs_err"] <= PARITY_TOL)
+    return out
 
 
 # --------------------------------------------------------------------------------------- helpers
@@ -171,18 +289,20 @@ class ClockSampler:
         return out
 
 
-def overlap_flops(chi, symmetric=True):
+def overlap_flops(chi_x, chi_y=None):
     """Algorithmic FLOPs of stage 2: per pair (y, x) and site k
-    8*(2*cy[k-1]*cx[k-1]*cx[k] + 2*cy[k-1]*cy[k]*cx[k]) with the actual bond dimensions."""
-    chi = np.asarray(chi, dtype=np.float64)
-    N, nb = chi.shape
-    tri = np.tril(np.ones((N, N))) if symmetric else np.ones((N, N))
+    8*(2*cy[k-1]*cx[k-1]*cx[k] + 2*cy[k-1]*cy[k]*cx[k]) with the actual bond dimensions; symmetric Gram
+    (chi_y None): pairs x <= y only."""
+    cx = np.asarray(chi_x, dtype=np.float64)
+    symmetric = chi_y is None
+    cy = cx if symmetric else np.asarray(chi_y, dtype=np.float64)
+    tri = np.tril(np.ones((cy.shape[0], cx.shape[0]))) if symmetric else None
     total = 0.0
-    for k in range(1, nb):
-        a = chi[:, k - 1]
-        t1 = np.outer(a, chi[:, k - 1] * chi[:, k])
-        t2 = np.outer(a * chi[:, k], chi[:, k])
-        total += 16.0 * float(((t1 + t2) * tri).sum())
+    for k in range(1, cx.shape[1]):
+        t1 = np.outer(cy[:, k - 1], cx[:, k - 1] * cx[:, k])
+        t2 = np.outer(cy[:, k - 1] * cy[:, k], cx[:, k])
+        t = t1 + t2
+        total += 16.0 * float((t * tri).sum() if symmetric else t.sum())
     return total
 
 
@@ -221,25 +341,23 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n, r, d, g, N = WORKLOADS[args.workload]
-    vals = []
-    last = None
+    last, vals, ests = None, [], []
     for _ in range(args.warmup):
         cpu_reference_sample(args.workload, budget_s=3.0)
-    t0 = time.perf_counter()
     for _ in range(args.steps):
         last = cpu_reference_sample(args.workload, budget_s=args.cpu_budget)
-        vals.append(last["value"])
-    wall = time.perf_counter() - t0
+        vals.append(last["value"]); ests.append(last["est_job_s"])
     v = float(np.mean(vals))
     line = {
         "impl": "reference", "metric": "gram_entries_per_sec", "value": v, "unit": "entries/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * float(np.mean(ests)),       # extrapolated time of the whole job on these cores
+        "sample_wall_ms_per_step": 1e3 * last["sample_wall_s"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "complex128 (f64)",
         "data": "synthetic", "gpu_launches": 0,
-        "config": {"workload": f"{args.workload}: {n} qubits, {r} layers, distance {d}, gamma {g}, {N} points, train Gram",
-                   "note": "CPU restatement of the reference (ITensors semantics, numpy/LAPACK); the reference's Julia "
-                           "and pytket-cutensornet backends do not install offline"},
+        "config": workload_config(args.workload),
+        "note": "CPU restatement of the reference (numpy/LAPACK, oracle/); the reference's Julia and pytket-cutensornet "
+                "backends do not install offline",
         "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": v, "unit": "entries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "circuits_per_s": last["circuits_per_s"],
@@ -251,17 +369,21 @@ def run_reference(args):
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    n, r, d, g, N = WORKLOADS[args.workload]
+    n, r, d, g, N, M = WORKLOADS[args.workload]
 
-    cpu_base = None
-    if world == 1 and not args.no_cpu_baseline:
-        cpu_base = cpu_reference_sample(args.workload, budget_s=args.cpu_budget)   # before CUDA init (fork pool)
+    # CPU work first (fork pools must not inherit a CUDA context): the bounded CPU baseline and the oracle side of
+    # the parity check, both on rank 0; the other ranks wait in the rendezvous.
+    cpu_base, pref = None, None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu_base = cpu_reference_sample(args.workload, budget_s=args.cpu_budget)
+    if rank == 0 and args.parity_states > 0:
+        pref = parity_reference(args.workload, args.parity_states)
 
     import torch
     import qkmps
     from qkmps.engine import SingleComm, build_gram
-    from qkmps.synth import entanglement_graph, synthetic_features
-    from gpu_backend.kernel_state_ansatz import KernelStateAnsatz, build_kernel_matrix
+    from qkmps.synth import entanglement_graph
+    from gpu_backend.kernel_state_ansatz import KernelStateAnsatz, build_kernel_matrix, _initial_cap
     qkmps.lib()
     if world > 1:
         from qkmps.comm import init_from_env
@@ -271,7 +393,7 @@ def run_ours(args):
         comm, device = SingleComm(), 0
     torch.cuda.set_device(device)
 
-    X = synthetic_features(N, n, 0)
+    X, Y = workload_inputs(args.workload)
     ans = KernelStateAnsatz(n, r, g, entanglement_graph(n, d))
     gates = ans.ansatz_circ.get_commands()
     plans = {}
@@ -279,16 +401,16 @@ def run_ours(args):
     def plan_factory(cap, early_exit=False, parallel=False):
         key = (cap, bool(early_exit), bool(parallel))
         if key not in plans:
-            plans[key] = qkmps.Plan(n, gates, qkmps.QK_TRUNC_PYTKET, 1e-16, cap,
+            plans[key] = qkmps.Plan(n, gates, qkmps.QK_TRUNC_PYTKET, TRUNC_ERROR, cap,
                                     (qkmps.QK_PLAN_EARLY_EXIT if early_exit else 0) |
                                     (qkmps.QK_PLAN_PARALLEL if parallel else 0))
         return plans[key]
 
-    from gpu_backend.kernel_state_ansatz import _initial_cap
-    cap0 = args.chi if args.chi > 0 else _initial_cap(ans, 1e-16)
+    cap0 = args.chi if args.chi > 0 else _initial_cap(ans, TRUNC_ERROR)
     X_dev = torch.from_numpy(X).to(f"cuda:{device}")
+    Y_dev = torch.from_numpy(Y).to(f"cuda:{device}") if M else None
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=f"cuda:{device}")
-    pairs = N * (N + 1) // 2
+    pairs = n_entries(N, M)
 
     def barrier():
         if world > 1:
@@ -296,19 +418,20 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def step_device():
-        return build_gram(comm, plan_factory, n, X_dev, None, chi_cap=cap0, device=device, return_device=True)
+        return build_gram(comm, plan_factory, n, X_dev, Y_dev, chi_cap=cap0, device=device, return_device=True)
 
     def step_e2e():
-        return build_kernel_matrix(comm, ans, X, truncation_error=1e-16, chi=cap0)
+        return build_kernel_matrix(comm, ans, X, Y, truncation_error=TRUNC_ERROR, chi=cap0)
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step_device()
         step_e2e()
 
     # ---- `value`: inputs resident in HBM, CUDA events, max over ranks
     sampler = ClockSampler(device)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sim_ms, gram_ms, launches, prof = [], [], 0, None
+    sim_ms, gram_ms, launches, prof, K_dev = [], [], 0, None, None
     barrier()
     if rank == 0:
         sampler.start()
@@ -316,13 +439,14 @@ def run_ours(args):
         flush.zero_()                      # L2 flush between timed iterations
         barrier()
         ev[k][0].record()
-        _, prof = step_device()
+        K_dev, prof = step_device()
         ev[k][1].record()
-        sim_ms.append(prof["sim_ms_x"]); gram_ms.append(prof["gram_ms"]); launches += prof["launches"]
+        sim_ms.append(prof["sim_ms_x"] + prof["sim_ms_y"]); gram_ms.append(prof["gram_ms"]); launches += prof["launches"]
     barrier()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     # ---- `e2e`: host buffers through the reference-facing entry point
     e2e_s = []
+    Kh = None
     for k in range(args.steps):
         flush.zero_()
         barrier()
@@ -345,6 +469,16 @@ def run_ours(args):
         launches = int(lt.item())
     else:
         sim_mean, gram_mean = float(np.mean(sim_ms)), float(np.mean(gram_ms))
+
+    # ---- parity of what was just timed (rank 0; the other ranks wait at the final barrier)
+    parity = None
+    if rank == 0 and pref is not None:
+        K_timed = K_dev.cpu().numpy()
+        parity = parity_check(K_timed, pref, args.workload, qkmps, ans, device, int(prof["chi_cap"]))
+        parity["e2e_vs_device_path_max_abs_diff"] = float(np.abs(Kh - K_timed).max())
+        parity["max_abs_err"] = max(parity["max_abs_err"], 0.0)
+    if world > 1:
+        comm.Barrier()
     if rank != 0:
         return
 
@@ -360,32 +494,39 @@ def run_ours(args):
         dmma_peak = qkmps.dmma_peak(device, 20000)
     except Exception:
         dmma_peak = None
-    # stage 2 flops of rank 0's tiles ~ total / world (row blocks are dealt evenly)
-    chi_all = info["chi"]
+    chi_x = info["chi"]
+    chi_y = prof["info_y"]["chi"] if M else None
     if world == 1:
-        f2 = overlap_flops(chi_all)
-    else:
-        f2 = overlap_flops(chi_all) * (N / max(hi - lo, 1)) ** 2 / world   # estimate from rank 0's shard
-    b1 = sim_bytes(chi_all, prof["plan_obj"].ops())
+        f2 = overlap_flops(chi_x, chi_y)
+    else:   # estimate from rank 0's shard(s); every rank computes 1/world of the pairs
+        scale_x = N / max(hi - lo, 1)
+        f2 = overlap_flops(chi_x, chi_y) * scale_x * (scale_x if not M else M / max(len(chi_y), 1)) / world
+    b1 = sim_bytes(chi_x, prof["plan_obj"].ops()) + (sim_bytes(chi_y, prof["plan_obj"].ops()) if M else 0.0)
+    gk = prof.get("gram_kernel", "qk_gram_dmma_kernel")
     stage2 = {"bound": "tensor", "achieved": f2 / (gram_mean * 1e-3) / 1e12, "peak": dmma_peak, "unit": "TFLOP/s",
               "frac": (f2 / (gram_mean * 1e-3) / 1e12 / dmma_peak) if dmma_peak else None, "traffic": None,
-              "kernel": "qk_gram_dmma_kernel", "ms": gram_mean,
+              "kernel": gk, "ms": gram_mean,
               "peak_source": "DMMA m8n8k4 FP64 microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 figure; "
-                             "nominal 37-40 TFLOP/s)",
+                             "architectural 148 SM x 4 x 512 flop / 16 clk x 1.965 GHz = 37.2 TFLOP/s)",
               "algorithmic_flops_per_launch": f2}
     stage1 = {"bound": "hbm", "achieved": b1 / (sim_mean * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
               "frac": b1 / (sim_mean * 1e-3) / 1e9 / hbm_peak, "traffic": None, "kernel": "qk_sim_kernel", "ms": sim_mean,
               "peak_source": hbm_src, "algorithmic_bytes_per_launch": b1,
-              "note": "stage 1 is bound by FP64 Jacobi-SVD arithmetic and barrier latency, not HBM: the algorithmic "
-                      "byte model of SURVEY.md 8(d) is reported as asked, see DESIGN.md"}
-    # DRAM traffic per launch from the committed ncu captures (valid for the default workload on one GPU)
-    try:
-        tr = json.load(open(ROOT / "profiles" / "r01_dram_traffic.json"))
+              "note": "SURVEY.md 8(d) byte model, reported as asked; the kernel's working set is L2-resident and it is "
+                      "bound by FP64 Jacobi arithmetic latency (see fp64 below and DESIGN.md 4.1)"}
+    try:   # per-launch ncu figures of the committed captures (valid for the default workload on one GPU)
+        tr = json.load(open(ROOT / "profiles" / "r02_ncu_counters.json"))
         if world == 1 and args.workload == "c3" and args.points == 0:
-            stage1["traffic"] = tr["qk_sim_kernel"]["dram_bytes"]
-            stage2["traffic"] = tr["qk_gram_dmma_kernel"]["dram_bytes"]
-            stage1["traffic_source"] = tr["qk_sim_kernel"]["capture"]
-            stage2["traffic_source"] = tr["qk_gram_dmma_kernel"]["capture"]
+            for st, key in ((stage1, "qk_sim_kernel"), (stage2, "qk_gram_dmma_kernel")):
+                if key in tr:
+                    st["traffic"] = tr[key].get("dram_bytes")
+                    st["traffic_source"] = tr[key].get("capture")
+            if "qk_sim_kernel" in tr and tr["qk_sim_kernel"].get("dfma_flops"):
+                fl = tr["qk_sim_kernel"]["dfma_flops"]
+                stage1["fp64"] = {"bound": "fp64_fma", "achieved": fl / (sim_mean * 1e-3) / 1e12, "peak": dmma_peak,
+                                  "unit": "TFLOP/s", "frac": fl / (sim_mean * 1e-3) / 1e12 / dmma_peak if dmma_peak else None,
+                                  "flops_per_launch": fl, "source": "ncu-counted FP64 instructions x 2 x 32 lanes "
+                                  "(profiles/r02_ncu_counters.json); peak = FP64 FMA peak = DMMA peak on B200"}
     except Exception:
         pass
     dominant = stage2 if gram_mean >= sim_mean else stage1
@@ -395,27 +536,30 @@ def run_ours(args):
 
     line = {
         "metric": "gram_entries_per_sec", "value": value, "unit": "entries/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "complex128 (f64)", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {n} qubits, {r} layers, distance {d}, gamma {g}, {N} points, full train "
-                               f"Gram ({pairs} unique entries)", "truncation_error": 1e-16, "trunc_rule": "pytket",
-                   "l2": f"flushed with a {L2_FLUSH_BYTES >> 20} MiB write between timed iterations; packed states "
-                         f"({prof['frag_bytes_per_state'][0] * N >> 20} MiB) exceed the 126 MB L2",
-                   "parallelism": f"datapoints sharded over {world} GPU(s); all-gather of packed states; row blocks of K "
-                                  "dealt to ranks",
-                   "stage1_schedule": prof.get("stage1_schedule", ""), "stage2_kernel": prof.get("gram_kernel", "")},
-        "circuits_per_s": N / (ms_per_step * 1e-3),
-        "stage_ms": {"simulate": sim_mean, "gram": gram_mean, "other": ms_per_step - sim_mean - gram_mean},
+        "config": workload_config(args.workload),
+        "details": {"packed_state_bytes": [int(v) for v in prof["frag_bytes_per_state"]],
+                    "parallelism": f"datapoints sharded over {world} GPU(s); {prof.get('exchange', 'all-gather of packed states')}",
+                    "stage1_schedule": prof.get("stage1_schedule", ""), "stage2_kernel": gk},
+        "circuits_per_s": (N + M) / (ms_per_step * 1e-3),
+        "stage_ms": {"simulate": sim_mean, "gram": gram_mean, "other": ms_per_step - sim_mean - gram_mean,
+                     "note": "kernel times on their own streams; stages may overlap, so 'other' can be negative"},
         "roofline": roofline, "stages": {"simulate": stage1, "gram": stage2},
-        "e2e": {"value": e2e_value, "unit": "entries/s", "h2d_bytes_per_step": int(X.nbytes),
-                "d2h_bytes_per_step": int(N * N * 8), "ms_per_step": 1e3 * e2e_tot / args.steps},
+        "e2e": {"value": e2e_value, "unit": "entries/s", "h2d_bytes_per_step": int(X.nbytes + (Y.nbytes if M else 0)),
+                "d2h_bytes_per_step": int((M if M else N) * N * 8), "ms_per_step": 1e3 * e2e_tot / args.steps},
         "gpu_launches": launches, "clocks": clocks,
-        "max_chi": int(chi_all.max()), "mean_max_chi": float(chi_all.max(axis=1).mean()),
+        "max_chi": int(chi_x.max()), "mean_max_chi": float(chi_x.max(axis=1).mean()),
+        "parity": parity,
     }
     if cpu_base is not None:
         line["cpu_baseline"] = {k: cpu_base[k] for k in ("value", "unit", "cores", "kind", "sample")}
         line["cpu_baseline"]["circuits_per_s"] = cpu_base["circuits_per_s"]
     print(json.dumps(line))
+    sys.stdout.flush()
+    if parity is not None and not parity["pass"]:
+        print(f"PARITY FAILURE: max_abs_err {parity['max_abs_err']:.3e} > {PARITY_TOL}", file=sys.stderr)
+        sys.exit(3)
 
 
 def main():
@@ -427,12 +571,13 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-budget", type=float, default=14.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity-states", type=int, default=32, help="states the oracle simulates for the parity check (0: off)")
     ap.add_argument("--chi", type=int, default=0, help="first bond cap tried (0: the backend's own choice)")
     ap.add_argument("--points", type=int, default=0, help="override the number of datapoints (experiments only)")
     args = ap.parse_args()
     if args.points > 0:
-        n, r, d, g, _ = WORKLOADS[args.workload]
-        WORKLOADS[args.workload] = (n, r, d, g, args.points)
+        n, r, d, g, _, M = WORKLOADS[args.workload]
+        WORKLOADS[args.workload] = (n, r, d, g, args.points, min(M, args.points))
     if args.impl == "reference":
         run_reference(args)
     else:

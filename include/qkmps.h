@@ -166,12 +166,18 @@ int qk_gram_lane(const qk_plan* plan, int device, void* stream, int max_chi,
 int qk_gram_store(const qk_batch* X, const qk_batch* Y_or_null, double* K_host, int64_t ldk, float* ms_out);
 
 /* ---- whole path with host buffers on one device: what build_kernel_matrix does per process.
- *      K_host is [Ny or Nx][ldk]. ---- */
+ *      K_host is [Ny or Nx][ldk].  The plan's chi_cap is used as is (no escalation): if any state wants a larger
+ *      bond dimension the call fails with QK_ERR_LIMIT instead of returning a hard-truncated kernel matrix
+ *      (the Python engine re-runs such states with the next cap of its ladder). ---- */
 int qk_gram_host(const qk_plan* plan, int device, const double* X_host, int Nx,
                  const double* Y_host_or_null, int Ny, int ldx, double* K_host, int64_t ldk);
 
 /* FP64 tensor-core (DMMA m8n8k4) peak microbenchmark: TFLOP/s over `iters` MMAs per warp */
 int qk_dmma_peak(int device, int iters, double* tflops);
+/* Do the FP64 tensor pipe (DMMA) and the FP64 FMA pipe (DFMA) run concurrently on one SM?  Four warps of every
+ * CTA issue DMMAs, four issue DFMAs; ms[0] = DMMA warps alone, ms[1] = DFMA warps alone, ms[2] = both.
+ * ms[2] ~ max(ms[0], ms[1]): independent pipes; ms[2] ~ ms[0] + ms[1]: one shared datapath. */
+int qk_pipe_mix(int device, int iters, float* ms /*[3]*/);
 
 #ifdef __cplusplus
 }

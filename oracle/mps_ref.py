@@ -77,7 +77,12 @@ def truncate_pytket(s: np.ndarray, truncation_fidelity: float, value_of_zero: fl
     m = int(np.sum(s >= value_of_zero)) if value_of_zero > 0 else len(s)
     m = max(m, 1)
     s = s[:m]
-    denom = float(np.sum(s * s))
+    # total weight summed in the same (sequential, largest first) order as the running sum below, so that
+    # numer == denom is reached as soon as the remaining values no longer change the sum -- a pairwise-summed
+    # total differs from the running sum in the last bit and would keep rounding-noise values (sigma ~ 1e-16)
+    denom = 0.0
+    for v in s:
+        denom += float(v) ** 2
     if denom == 0.0:
         return 1, 1.0
     if truncation_fidelity < 1.0:
@@ -91,7 +96,9 @@ def truncate_pytket(s: np.ndarray, truncation_fidelity: float, value_of_zero: fl
         k, numer = m, denom
     if chi is not None and k > chi:
         k = chi
-        numer = float(np.sum(s[:k] ** 2))
+        numer = 0.0
+        for v in s[:k]:
+            numer += float(v) ** 2
     return k, numer / denom
 
 

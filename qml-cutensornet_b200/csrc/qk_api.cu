@@ -695,6 +695,17 @@ int qk_gram_lane(const qk_plan* plan, int device, void* stream_v, int max_chi, c
 }
 
 // ---------------------------------------------------------------- whole path, host buffers
+// OR of the stage-1 flags of every state of a batch
+static int batch_flags_or(const qk_batch* b, int* flags_or) {
+  *flags_or = 0;
+  if (!b || b->N == 0) return QK_OK;
+  std::vector<QkStat> st(b->N);
+  QK_CUDA(cudaSetDevice(b->device), "cudaSetDevice");
+  QK_CUDA(cudaMemcpy(st.data(), b->stats, st.size() * sizeof(QkStat), cudaMemcpyDeviceToHost), "copy stats");
+  for (const QkStat& q : st) *flags_or |= q.flags;
+  return QK_OK;
+}
+
 int qk_gram_host(const qk_plan* plan, int device, const double* X_host, int Nx, const double* Y_host, int Ny, int ldx,
                  double* K_host, int64_t ldk) {
   if (!plan || !X_host || !K_host || Nx < 1) return fail(QK_ERR_ARG, "bad arguments");
@@ -704,6 +715,16 @@ int qk_gram_host(const qk_plan* plan, int device, const double* X_host, int Nx, 
   qk_batch *bx = nullptr, *by = nullptr;
   int rc = qk_simulate(plan, device, X_host, Nx, ldx, &bx);
   if (rc == QK_OK && !sym) rc = qk_simulate(plan, device, Y_host, Ny, ldx, &by);
+  // The plan's bond cap is fixed here (no escalation, unlike the Python engine): a state that wanted more than
+  // the cap was hard-truncated, so the Gram matrix would be wrong -- refuse instead of returning it.
+  for (qk_batch* b : {bx, by}) {
+    int fl = 0;
+    if (rc == QK_OK) rc = batch_flags_or(b, &fl);
+    if (rc == QK_OK && (fl & QK_FLAG_CAP_HIT))
+      rc = fail(QK_ERR_LIMIT, "a state's bond dimension exceeds the plan's chi_cap: re-create the plan with a larger cap");
+    if (rc == QK_OK && (fl & QK_FLAG_NO_CONVERGE))
+      rc = fail(QK_ERR_CUDA, "Jacobi SVD hit its sweep limit (stage 1 did not converge)");
+  }
   void *fx = nullptr, *fy = nullptr;
   double* K_dev = nullptr;
   const int n = plan->n;
@@ -754,6 +775,13 @@ int qk_dmma_peak(int device, int iters, double* tflops) {
   if (!tflops || iters < 1) return fail(QK_ERR_ARG, "bad arguments");
   QK_CUDA(cudaSetDevice(device), "cudaSetDevice");
   QK_CUDA(qk_run_dmma_peak(iters, tflops), "dmma peak kernel");
+  return QK_OK;
+}
+
+int qk_pipe_mix(int device, int iters, float* ms) {
+  if (!ms || iters < 1) return fail(QK_ERR_ARG, "bad arguments");
+  QK_CUDA(cudaSetDevice(device), "cudaSetDevice");
+  QK_CUDA(qk_run_pipe_mix(iters, ms), "pipe mix kernel");
   return QK_OK;
 }
 

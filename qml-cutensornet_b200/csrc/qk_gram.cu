@@ -827,3 +827,69 @@ cudaError_t qk_run_dmma_peak(int iters, double* tflops) {
   *tflops = flops / (best * 1e-3) / 1e12;
   return cudaGetLastError();
 }
+
+// ------------------------------------------------------------------------------------------------
+// Pipe co-issue microbenchmark: warps 0-3 of a CTA (one per scheduler) issue DMMAs, warps 4-7 DFMAs.
+// Per iteration a DMMA warp occupies its pipe for 8 x 16 cycles and a DFMA warp for 64 x 2 cycles.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) qk_pipe_mix_kernel(int iters, int mode, double* sink) {
+  const int warp = threadIdx.x >> 5;
+  double s = 0.0;
+  if (warp < 4) {
+    if (mode & 1) {
+      double acc[8][2];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+      const double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) qk_dmma(acc[i], a, b);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += acc[i][0] + acc[i][1];
+    }
+  } else if (mode & 2) {
+    double acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 1e-3 * (threadIdx.x + i);
+    const double a = 1.0 + 1e-9 * threadIdx.x, b = 1e-9 * threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int rep = 0; rep < 4; ++rep)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = fma(acc[i], a, b);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i];
+  }
+  if (s == 123.456) sink[0] = s;
+}
+
+cudaError_t qk_run_pipe_mix(int iters, float* ms3) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  double* sink = nullptr;
+  cudaError_t e = cudaMalloc(&sink, sizeof(double));
+  if (e != cudaSuccess) return e;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  qk_pipe_mix_kernel<<<sms, 256>>>(iters / 8 + 1, 3, sink);   // warm-up
+  for (int mode = 1; mode <= 3 && e == cudaSuccess; ++mode) {
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+      cudaEventRecord(e0);
+      qk_pipe_mix_kernel<<<sms, 256>>>(iters, mode, sink);
+      cudaEventRecord(e1);
+      e = cudaEventSynchronize(e1);
+      if (e != cudaSuccess) break;
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (ms < best) best = ms;
+    }
+    ms3[mode - 1] = best;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(sink);
+  return e != cudaSuccess ? e : cudaGetLastError();
+}

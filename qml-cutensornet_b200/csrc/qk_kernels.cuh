@@ -83,3 +83,4 @@ cudaError_t qk_launch_gram_store(int n, const c128* storeX, int64_t strideX, con
                                  double* K, int64_t ldk, cudaStream_t stream);
 
 cudaError_t qk_run_dmma_peak(int iters, double* tflops);
+cudaError_t qk_run_pipe_mix(int iters, float* ms3);

@@ -441,8 +441,12 @@ QK_DEV void qk_jacobi(SimCtx& c, int R, int C) {
 //   ITensors  NDTensors truncate!: drop from the tail while discarded + p <= cutoff * sum(p)
 //   pytket    drop sigma < value_of_zero, keep the shortest head with numer/denom >= fidelity, renormalise
 // ------------------------------------------------------------------------------------------------
-QK_DEV void qk_truncate(SimCtx& c, int C, int capb) {
+QK_DEV void qk_truncate(SimCtx& c, int C, int capb, int bond) {
   const SimParams* P = c.P;
+  // a cap equal to the chain-edge rank bound 2^min(b, n-b) is structural, not a limit of the kernel: anything the
+  // rule wants to keep beyond it is rounding noise (e.g. cutoff = 0), so QK_FLAG_CAP_HIT is not raised for it
+  const int edge_e = bond < P->n - bond ? bond : P->n - bond;
+  const bool cap_is_edge = edge_e < 30 && capb >= (1 << edge_e);
   int k;
   double renorm = 1.0;
   if (P->mode == 0) {
@@ -455,7 +459,7 @@ QK_DEV void qk_truncate(SimCtx& c, int C, int capb) {
       const double scale = (total == 0.0) ? 1.0 : total;
       while (k > 1 && err + c.nrm2[c.order[k - 1]] <= P->cutoff * scale) { err += c.nrm2[c.order[k - 1]]; --k; }
       if (k > capb) {
-        c.sh->flags |= QK_FLAG_CAP_HIT;
+        if (!cap_is_edge) c.sh->flags |= QK_FLAG_CAP_HIT;
         while (k > capb) { err += c.nrm2[c.order[k - 1]]; --k; }
       }
       c.sh->trunc_weight += err / scale;
@@ -477,7 +481,7 @@ QK_DEV void qk_truncate(SimCtx& c, int C, int capb) {
         if (k < 1) { numer = c.nrm2[c.order[0]]; k = 1; }
       } else { k = m; numer = denom; }
       if (k > capb) {
-        c.sh->flags |= QK_FLAG_CAP_HIT;
+        if (!cap_is_edge) c.sh->flags |= QK_FLAG_CAP_HIT;
         k = capb;
         numer = 0.0;
         for (int t = 0; t < k; ++t) numer += c.nrm2[c.order[t]];
@@ -579,7 +583,7 @@ QK_DEV void qk_op_2q(SimCtx& c, const QkOp& op) {
   QK_PAR_END
   QK_PAR_BEGIN(tid)
     if (tid == 0) {
-      qk_truncate(c, C, c.P->cap[k + 1]);
+      qk_truncate(c, C, c.P->cap[k + 1], k + 1);
       // The new tensor is staged behind W.  If W (R x C) plus the staging area (keep x C) exceed the
       // region, the kept columns are first compacted to the front of W by column swaps (sorted order);
       // otherwise they are addressed through order[].  pos[j] = where original column j is now,
@@ -936,7 +940,7 @@ QK_DEV void qk_op_2q_b(SimCtx& c, const QkOp& op) {
     }
   QK_PAR_END
   QK_PAR_BEGIN(tid)
-    if (tid == 0) qk_truncate(c, C, c.P->cap[k + 1]);
+    if (tid == 0) qk_truncate(c, C, c.P->cap[k + 1], k + 1);
   QK_PAR_END
   const int keep = c.sh->keep;
   const double renorm = c.sh->renorm;

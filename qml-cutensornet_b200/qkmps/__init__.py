@@ -61,7 +61,7 @@ EXPORTS = [
     "qk_simulate", "qk_simulate_dev", "qk_simulate_trace", "qk_batch_sim_ms", "qk_batch_size", "qk_batch_info", "qk_batch_export",
     "qk_batch_import", "qk_batch_max_chi", "qk_batch_destroy", "qk_frag_stride", "qk_batch_pack",
     "qk_batch_pack_scatter",
-    "qk_gram_frags", "qk_batch_store", "qk_gram_lane", "qk_gram_store", "qk_gram_host", "qk_dmma_peak",
+    "qk_gram_frags", "qk_batch_store", "qk_gram_lane", "qk_gram_store", "qk_gram_host", "qk_dmma_peak", "qk_pipe_mix",
 ]
 
 _lib = None
@@ -361,3 +361,10 @@ def dmma_peak(device: int = 0, iters: int = 20000) -> float:
     out = ctypes.c_double()
     _check(lib().qk_dmma_peak(int(device), int(iters), ctypes.byref(out)))
     return out.value
+
+
+def pipe_mix(device: int = 0, iters: int = 20000):
+    """(ms DMMA warps alone, ms DFMA warps alone, ms both) -- do the FP64 tensor and FMA pipes overlap?"""
+    out = (ctypes.c_float * 3)()
+    _check(lib().qk_pipe_mix(int(device), int(iters), out))
+    return tuple(float(v) for v in out)

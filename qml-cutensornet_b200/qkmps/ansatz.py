@@ -148,6 +148,8 @@ def expected_chi(gamma: float, structural: int, truncation_error: float = 1e-16,
     costs a partial run plus a re-run of the datapoints that hit the cap (engine._simulate_shard).
     """
     theta = (math.pi / 2) * gamma * gamma
+    if theta <= 0.0:
+        return 1          # gamma = 0: no interaction at all, product state
     if theta >= 1.0 or truncation_error <= 0 or n_terms > 4:
         return structural
     k = math.log(max(truncation_error, 1e-300)) / math.log(theta * theta)

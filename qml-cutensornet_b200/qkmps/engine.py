@@ -225,17 +225,33 @@ def build_gram(comm, plan_factory, n_qubits, X, Y=None, chi_cap=16, device=None,
     t_all = time.perf_counter()
     launches = 0
 
-    # ---- stage 1 on this rank's shard(s)
+    # ---- stage 1 on this rank's shard(s).  A failure here (bond dimension above the kernels' limit, CUDA error) is
+    # rank-local and data dependent: it is carried through the collective below and raised on EVERY rank, so that
+    # the other ranks do not block forever in all_reduce / all_gather.
     lo, hi = shard_bounds(Nx, size, rank)
-    sx = _simulate_shard(plan_factory, X[lo:hi], device, chi_cap, comm, n_qubits)
-    info_x = sx.info()
-    sy, info_y = None, None
-    if not symmetric:
-        if not isinstance(Y, torch.Tensor):
-            Y = np.asarray(Y, dtype=np.float64)
-        ylo, yhi = shard_bounds(Ny, size, rank)
-        sy = _simulate_shard(plan_factory, Y[ylo:yhi], device, chi_cap, comm, n_qubits)
-        info_y = sy.info()
+    sy, info_y, local_err = None, None, None
+    try:
+        sx = _simulate_shard(plan_factory, X[lo:hi], device, chi_cap, comm, n_qubits)
+        info_x = sx.info()
+        if not symmetric:
+            if not isinstance(Y, torch.Tensor):
+                Y = np.asarray(Y, dtype=np.float64)
+            ylo, yhi = shard_bounds(Ny, size, rank)
+            sy = _simulate_shard(plan_factory, Y[ylo:yhi], device, chi_cap, comm, n_qubits)
+            info_y = sy.info()
+        for inf in (info_x, info_y):
+            if inf is not None and len(inf["flags"]) and np.any(inf["flags"] & QK_FLAG_NO_CONVERGE):
+                raise QkError(-2, "stage 1: the Jacobi SVD hit its sweep limit on at least one state")
+    except QkError as e:
+        if size == 1:
+            raise
+        local_err = e
+    if size > 1:
+        codes = allreduce_max_array(comm, np.array([0 if local_err is None else -int(local_err.code)], dtype=np.int32))
+        if int(codes[0]) != 0:
+            if local_err is not None:
+                raise local_err
+            raise QkError(-int(codes[0]), "stage 1 failed on another rank (see that rank's error)")
     prof["sim_ms_x"] = sx.sim_ms
     prof["sim_ms_y"] = sy.sim_ms if sy is not None else 0.0
     prof["chi_cap"] = max(sx.cap, sy.cap if sy is not None else 1)
@@ -330,6 +346,5 @@ def build_gram(comm, plan_factory, n_qubits, X, Y=None, chi_cap=16, device=None,
         out = K if return_device else K.cpu().numpy()
     torch.cuda.synchronize()
     prof["total_s"] = time.perf_counter() - t_all
-    bad = int(np.any(info_x["flags"] & QK_FLAG_NO_CONVERGE)) if len(info_x["flags"]) else 0
-    prof["no_converge"] = bad
+    prof["no_converge"] = 0   # a sweep-limit hit raises above (on every rank)
     return out, prof
