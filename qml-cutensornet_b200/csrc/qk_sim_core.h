@@ -327,10 +327,11 @@ __device__ __forceinline__ void qk_pair_step_generic(c128* wp, c128* wq, int R, 
 }
 #endif
 
+// One sweep (every round of the round-robin tournament) of one-sided Jacobi on the R x C matrix W (column-major,
+// leading dimension ldw).  Sets c.sh->rotated when a rotation above QK_QUAD_EPS was applied.  Shared by the
+// shared-memory-resident path (qk_jacobi) and the column-block visits of the large-matrix path (qk_sim_big.h).
 template <int G>
-QK_DEV void qk_jacobi(SimCtx& c, int R, int C) {
-  c128* W = c.W;
-  const int ldw = R;
+QK_DEV void qk_jacobi_sweep(SimCtx& c, c128* W, int ldw, int R, int C, double tol2, double floor2, double abs2) {
   const int Ce = (C + 1) & ~1;
   const int npairs = Ce / 2;
   const int nrounds = Ce - 1;
@@ -340,6 +341,70 @@ QK_DEV void qk_jacobi(SimCtx& c, int R, int C) {
   const int npass = (npairs + pp - 1) / pp;
   const int rpt = (R + tpp - 1) / tpp;   // rows per thread
   (void)rpt;
+  for (int r = 0; r < nrounds; ++r) {
+    for (int pass = 0; pass < npass; ++pass) {
+#if defined(__CUDA_ARCH__) && !defined(QK_HOST_EMU)
+      // device: rows kept in registers, partial dot products reduced with warp shuffles -> one barrier per round
+      QK_PAR_BEGIN(tid)
+        const int ps = tid / tpp, sl = tid - ps * tpp;
+        const int i = pass * pp + ps;
+        int p = 0, q = 0;
+        const bool valid = (i < npairs) && qk_rr_pair(i, r, Ce, C, p, q);
+        c128* wp = W + (size_t)p * ldw;
+        c128* wq = W + (size_t)q * ldw;
+        if (rpt <= 1) qk_pair_step<1>(wp, wq, R, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
+        else if (rpt <= 2) qk_pair_step<2>(wp, wq, R, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
+        else if (rpt <= 4) qk_pair_step<4>(wp, wq, R, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
+        else if (rpt <= 8 && G != 128) qk_pair_step<8>(wp, wq, R, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
+        else qk_pair_step_generic(wp, wq, R, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
+      QK_PAR_END
+#else
+      QK_PAR_BEGIN(tid)
+        const int ps = tid / tpp, sl = tid - ps * tpp;
+        const int i = pass * pp + ps;
+        int p = 0, q = 0;
+        const bool valid = (i < npairs) && qk_rr_pair(i, r, Ce, C, p, q);
+        double a = 0, b = 0, gr = 0, gi = 0;
+        if (valid) {
+          const c128* wp = W + (size_t)p * ldw;
+          const c128* wq = W + (size_t)q * ldw;
+          for (int row = sl; row < R; row += tpp) {
+            const c128 xp = wp[row], xq = wq[row];
+            a += xp.x * xp.x + xp.y * xp.y;
+            b += xq.x * xq.x + xq.y * xq.y;
+            gr += xp.x * xq.x + xp.y * xq.y;   // gamma = conj(xp) * xq
+            gi += xp.x * xq.y - xp.y * xq.x;
+          }
+        }
+        c.scr[4 * tid + 0] = a; c.scr[4 * tid + 1] = b; c.scr[4 * tid + 2] = gr; c.scr[4 * tid + 3] = gi;
+      QK_PAR_END
+      QK_PAR_BEGIN(tid)
+        const int ps = tid / tpp, sl = tid - ps * tpp;
+        const int i = pass * pp + ps;
+        int p = 0, q = 0;
+        const bool valid = (i < npairs) && qk_rr_pair(i, r, Ce, C, p, q);
+        if (valid) {
+          double a = 0, b = 0, gr = 0, gi = 0;
+          for (int t = 0; t < tpp; ++t) {
+            const double* s4 = c.scr + 4 * (ps * tpp + t);
+            a += s4[0]; b += s4[1]; gr += s4[2]; gi += s4[3];
+          }
+          double cs; c128 f;
+          const int rot = qk_rotation(a, b, gr, gi, tol2, floor2, abs2, cs, f);
+          if (rot) {
+            qk_rotate_rows(W + (size_t)p * ldw, W + (size_t)q * ldw, R, sl, tpp, cs, f);
+            if (sl == 0 && rot == 2) c.sh->rotated = 1;
+          }
+        }
+      QK_PAR_END
+#endif
+    }
+  }
+}
+
+template <int G>
+QK_DEV void qk_jacobi(SimCtx& c, int R, int C) {
+  c128* W = c.W;
   const double tol2 = c.P->tol * c.P->tol;
   int sweep = 0;
   // total weight (Frobenius norm^2) -- invariant under the rotations
@@ -361,65 +426,7 @@ QK_DEV void qk_jacobi(SimCtx& c, int R, int C) {
   const double abs2 = c.P->abs_rel * c.P->abs_rel * total * total;
   if (C >= 2) {
     for (; sweep < c.P->max_sweeps; ++sweep) {
-      for (int r = 0; r < nrounds; ++r) {
-        for (int pass = 0; pass < npass; ++pass) {
-#if defined(__CUDA_ARCH__) && !defined(QK_HOST_EMU)
-          // device: rows kept in registers, partial dot products reduced with warp shuffles -> one barrier per round
-          QK_PAR_BEGIN(tid)
-            const int ps = tid / tpp, sl = tid - ps * tpp;
-            const int i = pass * pp + ps;
-            int p = 0, q = 0;
-            const bool valid = (i < npairs) && qk_rr_pair(i, r, Ce, C, p, q);
-            c128* wp = W + (size_t)p * ldw;
-            c128* wq = W + (size_t)q * ldw;
-            if (rpt <= 1) qk_pair_step<1>(wp, wq, R, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
-            else if (rpt <= 2) qk_pair_step<2>(wp, wq, R, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
-            else if (rpt <= 4) qk_pair_step<4>(wp, wq, R, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
-            else if (rpt <= 8 && G != 128) qk_pair_step<8>(wp, wq, R, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
-            else qk_pair_step_generic(wp, wq, R, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
-          QK_PAR_END
-#else
-          QK_PAR_BEGIN(tid)
-            const int ps = tid / tpp, sl = tid - ps * tpp;
-            const int i = pass * pp + ps;
-            int p = 0, q = 0;
-            const bool valid = (i < npairs) && qk_rr_pair(i, r, Ce, C, p, q);
-            double a = 0, b = 0, gr = 0, gi = 0;
-            if (valid) {
-              const c128* wp = W + (size_t)p * ldw;
-              const c128* wq = W + (size_t)q * ldw;
-              for (int row = sl; row < R; row += tpp) {
-                const c128 xp = wp[row], xq = wq[row];
-                a += xp.x * xp.x + xp.y * xp.y;
-                b += xq.x * xq.x + xq.y * xq.y;
-                gr += xp.x * xq.x + xp.y * xq.y;   // gamma = conj(xp) * xq
-                gi += xp.x * xq.y - xp.y * xq.x;
-              }
-            }
-            c.scr[4 * tid + 0] = a; c.scr[4 * tid + 1] = b; c.scr[4 * tid + 2] = gr; c.scr[4 * tid + 3] = gi;
-          QK_PAR_END
-          QK_PAR_BEGIN(tid)
-            const int ps = tid / tpp, sl = tid - ps * tpp;
-            const int i = pass * pp + ps;
-            int p = 0, q = 0;
-            const bool valid = (i < npairs) && qk_rr_pair(i, r, Ce, C, p, q);
-            if (valid) {
-              double a = 0, b = 0, gr = 0, gi = 0;
-              for (int t = 0; t < tpp; ++t) {
-                const double* s4 = c.scr + 4 * (ps * tpp + t);
-                a += s4[0]; b += s4[1]; gr += s4[2]; gi += s4[3];
-              }
-              double cs; c128 f;
-              const int rot = qk_rotation(a, b, gr, gi, tol2, floor2, abs2, cs, f);
-              if (rot) {
-                qk_rotate_rows(W + (size_t)p * ldw, W + (size_t)q * ldw, R, sl, tpp, cs, f);
-                if (sl == 0 && rot == 2) c.sh->rotated = 1;
-              }
-            }
-          QK_PAR_END
-#endif
-        }
-      }
+      qk_jacobi_sweep<G>(c, W, R, R, C, tol2, floor2, abs2);
       const int rot = c.sh->rotated;
       QK_BARRIER();
       if (!rot) { ++sweep; break; }

