@@ -25,7 +25,7 @@ typedef enum {
   QK_OK = 0,
   QK_ERR_ARG = -1,       /* bad argument (also: unknown gate -- cpu_backend/kernel_state_ansatz.py:129, KernelPkg.jl:62) */
   QK_ERR_CUDA = -2,      /* CUDA runtime / launch failure, or no device */
-  QK_ERR_LIMIT = -3,     /* bond dimension above what the shared-memory-resident kernels support */
+  QK_ERR_LIMIT = -3,     /* bond dimension above what the kernels support (chi_cap <= 256), or above a plan's cap */
   QK_ERR_ALLOC = -4
 } qk_status;
 
@@ -69,6 +69,9 @@ typedef enum {
                                      same bond are multiplied into one SVD and SWAP pairs cancel) */
 #define QK_PLAN_PARALLEL 8        /* stage 1 in B (Vidal/Hastings) form: no gauge moves; ops levelised by the sites
                                      they touch so that independent bonds of one datapoint are updated concurrently */
+
+#define QK_PLAN_BIG 16            /* force the large-matrix stage-1 kernel (theta in global memory, block Jacobi, one
+                                     CTA cluster per datapoint) that plans with chi_cap > 32 use anyway; tests */
 
 typedef struct qk_plan qk_plan;     /* compiled static op schedule of one ansatz (host object) */
 typedef struct qk_batch qk_batch;   /* device-resident batch of simulated MPS */
@@ -162,7 +165,22 @@ int qk_gram_lane(const qk_plan* plan, int device, void* stream, int max_chi,
                  const void* storeY, const int32_t* chiY, int Ny,
                  const int32_t* tiles /*[n_tiles][4] = r0,r1,c0,c1*/, int n_tiles, int symmetric,
                  double* K_dev, int64_t ldk, float* ms_out);
-/* CUDA-core FP64 cross-check kernel working on the unpadded stores (any chi <= cap) */
+/* Same Gram tiles for ANY bond dimension (the path of BASELINE config 4, chi ~ 100): the transfer sweep of every
+ * (y, x) pair as two batched complex GEMMs per site on the FP64 tensor cores (DMMA), E and T of the pairs in
+ * global memory, site tensors read from the unpadded stores laid out by `plan`.  dims_x / dims_y: per-bond maxima
+ * of the bond dimensions over the X / Y states, [n+1] host ints (NULL: the plan's bond caps) -- they size the
+ * scratch buffers and the launch grids.  Replaces the same reference calls as qk_gram_frags. */
+int qk_gram_big(const qk_plan* plan, int device, void* stream, const int32_t* dims_x, const int32_t* dims_y,
+                const void* storeX, const int32_t* chiX, int Nx, const void* storeY, const int32_t* chiY, int Ny,
+                const int32_t* tiles /*[n_tiles][4] = r0,r1,c0,c1*/, int n_tiles, int symmetric,
+                double* K_dev, int64_t ldk, float* ms_out);
+/* Copies the states of `batch` into a store laid out for `plan` (its bond caps define the site slots) with the chi
+ * rows alongside: state i goes to position dst_index[i] (negative: skipped; NULL: i).  Merges batches simulated
+ * with different bond caps into the one buffer that is exchanged between ranks (replaces pickling MPS objects of
+ * different sizes, gpu_backend/kernel_state_ansatz.py:346-352,416-419).  Every copied state must fit the caps. */
+int qk_batch_repack(const qk_batch* batch, const qk_plan* plan, void* store_dev, int32_t* chi_dev,
+                    const int32_t* dst_index, void* stream);
+/* FP64 cross-check on the unpadded stores: CUDA cores for chi <= 32, the batched-GEMM sweep above */
 int qk_gram_store(const qk_batch* X, const qk_batch* Y_or_null, double* K_host, int64_t ldk, float* ms_out);
 
 /* ---- whole path with host buffers on one device: what build_kernel_matrix does per process.

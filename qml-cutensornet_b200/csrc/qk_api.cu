@@ -240,6 +240,33 @@ int qk_simulate_dev(const qk_plan* plan, int device, void* stream_v, const doubl
   QK_TRY(cudaEventRecord(e0, stream), "cudaEventRecord");
   double* lam_dev = nullptr; int32_t* lvl_dev = nullptr; QkStat* parts_dev = nullptr;
   P.parallel = plan->parallel; P.lam = nullptr; P.lam_ld = plan->rmax / 2; P.level_start = nullptr; P.n_levels = 0;
+  P.big_w = nullptr; P.big_s = nullptr; P.big_w_stride = P.big_s_stride = 0; P.big_flag = nullptr; P.big_jb = plan->jb;
+  P.unit_clk = nullptr;
+  if (plan->big) {
+    // large-matrix path: theta and the staging area of every resident cluster live in global memory
+    int ncta_req = 0, ncta = 1, n_clusters = 1;
+    if (const char* ev = getenv("QK_BIG_CLUSTER")) { const int v = atoi(ev); if (v >= 1 && v <= 16) ncta_req = v; }
+    c128 *w_dev = nullptr, *s_dev = nullptr; int* f_dev = nullptr;
+    cudaError_t ea = qk_sim_big_config(plan->smem_bytes, N, ncta_req, &ncta, &n_clusters);
+    const size_t w_stride = (size_t)plan->rmax * plan->rmax, s_stride = w_stride / 2;
+    if (ea == cudaSuccess) ea = pool_alloc_t(&w_dev, (size_t)n_clusters * w_stride * sizeof(c128));
+    if (ea == cudaSuccess) ea = pool_alloc_t(&s_dev, (size_t)n_clusters * s_stride * sizeof(c128));
+    if (ea == cudaSuccess) ea = pool_alloc_t(&f_dev, (size_t)n_clusters * 4 * sizeof(int));
+    if (ea == cudaSuccess) ea = cudaMemsetAsync(f_dev, 0, (size_t)n_clusters * 4 * sizeof(int), stream);
+    if (ea == cudaSuccess) {
+      P.big_w = w_dev; P.big_s = s_dev; P.big_w_stride = (int64_t)w_stride; P.big_s_stride = (int64_t)s_stride; P.big_flag = f_dev;
+      ea = qk_launch_sim_big(P, plan->smem_bytes, ncta, n_clusters, stream);
+      b->sim_grid = n_clusters * ncta;
+    }
+    if (ea == cudaSuccess) ea = cudaEventRecord(e1, stream);
+    if (ea == cudaSuccess) ea = cudaEventSynchronize(e1);
+    pool_free(w_dev); pool_free(s_dev); pool_free(f_dev);
+    if (ea != cudaSuccess) { cleanup(); qk_batch_destroy(b); return cuda_fail(ea, "stage-1 kernel (large-matrix path)"); }
+    cudaEventElapsedTime(&b->sim_ms, e0, e1);
+    cleanup();
+    *out = b;
+    return QK_OK;
+  }
   if (plan->parallel) {
     int ncta = 6;   // C3 levels are 12 or 24 items wide: 6 CTAs leave no idle CTA in the last round (measured 6.1 vs 6.7 ms with 8)
     if (const char* ev = getenv("QK_SIM_CLUSTER")) { const int v = atoi(ev); if (v >= 1 && v <= 8) ncta = v; }
@@ -598,6 +625,11 @@ int qk_gram_frags(int device, void* stream_v, int n_qubits, const int32_t* Dx, c
   return QK_OK;
 }
 
+static int gram_big_run(int device, cudaStream_t stream, int n, const int64_t* soff_x, const int64_t* soff_y,
+                        const int32_t* dims_x, const int32_t* dims_y, const c128* storeX, int64_t strideX,
+                        const int32_t* chiX, int Nx, const c128* storeY, int64_t strideY, const int32_t* chiY, int Ny,
+                        const int32_t* tiles, int n_tiles, int symmetric, double* K_dev, int64_t ldk, float* ms_out);
+
 int qk_gram_store(const qk_batch* X, const qk_batch* Y, double* K_host, int64_t ldk, float* ms_out) {
   if (!X || !K_host) return fail(QK_ERR_ARG, "NULL argument");
   if (!Y) Y = X;
@@ -607,6 +639,24 @@ int qk_gram_store(const qk_batch* X, const qk_batch* Y, double* K_host, int64_t 
   QK_CUDA(cudaSetDevice(X->device), "cudaSetDevice");
   double* K_dev = nullptr;
   QK_CUDA(pool_alloc_t(&K_dev, (size_t)Y->N * X->N * sizeof(double)), "cudaMalloc(K)");
+  if (std::max(X->chi_cap, Y->chi_cap) > 32) {
+    // E and T of a pair no longer fit in shared memory: batched-GEMM sweep on the same stores
+    const int32_t tile[4] = {0, Y->N, 0, X->N};
+    float ms = 0.f;
+    int rc = gram_big_run(X->device, nullptr, X->n, X->site_off.data(), Y->site_off.data(), X->cap.data(), Y->cap.data(),
+                          X->store, X->state_stride, X->chi, X->N, Y->store, Y->state_stride, Y->chi, Y->N, tile, 1, 0,
+                          K_dev, X->N, &ms);
+    if (rc == QK_OK) {
+      cudaError_t ec = cudaMemcpy2D(K_host, ldk * sizeof(double), K_dev, X->N * sizeof(double), X->N * sizeof(double), Y->N,
+                                    cudaMemcpyDeviceToHost);
+      if (ec != cudaSuccess) rc = cuda_fail(ec, "cudaMemcpy2D(K)");
+    }
+    std::string keep = g_err;
+    pool_free(K_dev);
+    g_err = keep;
+    if (ms_out) *ms_out = ms;
+    return rc;
+  }
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0, 0);
@@ -691,6 +741,99 @@ int qk_gram_lane(const qk_plan* plan, int device, void* stream_v, int max_chi, c
   pool_free(dbuf);
   if (e != cudaSuccess) return cuda_fail(e, "lane-per-pair Gram kernel");
   if (ms_out) *ms_out = ms;
+  return QK_OK;
+}
+
+
+// ---------------------------------------------------------------- stage 2, any bond dimension (batched DMMA GEMMs)
+static int gram_big_run(int device, cudaStream_t stream, int n, const int64_t* soff_x, const int64_t* soff_y,
+                        const int32_t* dims_x, const int32_t* dims_y, const c128* storeX, int64_t strideX,
+                        const int32_t* chiX, int Nx, const c128* storeY, int64_t strideY, const int32_t* chiY, int Ny,
+                        const int32_t* tiles, int n_tiles, int symmetric, double* K_dev, int64_t ldk, float* ms_out) {
+  QK_CUDA(cudaSetDevice(device), "cudaSetDevice");
+  std::vector<int2> pairs;
+  for (int t = 0; t < n_tiles; ++t) {
+    const int r0 = tiles[4 * t], r1 = tiles[4 * t + 1], c0 = tiles[4 * t + 2], c1 = tiles[4 * t + 3];
+    if (r0 < 0 || c0 < 0 || r1 > Ny || c1 > Nx || r0 > r1 || c0 > c1) return fail(QK_ERR_ARG, "tile out of range");
+    for (int y = r0; y < r1; ++y)
+      for (int x = c0; x < c1; ++x)
+        if (!symmetric || x <= y) pairs.push_back(make_int2(y, x));
+  }
+  if (pairs.empty()) { if (ms_out) *ms_out = 0.f; return QK_OK; }
+  int64_t emax = 1, tmax = 2;
+  for (int b = 0; b < n; ++b) {
+    emax = std::max<int64_t>(emax, (int64_t)dims_y[b] * dims_x[b]);
+    emax = std::max<int64_t>(emax, (int64_t)dims_y[b + 1] * dims_x[b + 1]);
+    tmax = std::max<int64_t>(tmax, (int64_t)dims_y[b] * 2 * dims_x[b + 1]);
+  }
+  size_t budget = (size_t)6 << 30;   // bytes of E + T scratch per chunk of pairs
+  if (const char* ev = getenv("QK_GRAM_BIG_SCRATCH_MB")) { const long v = atol(ev); if (v > 0) budget = (size_t)v << 20; }
+  size_t chunk = budget / ((size_t)(emax + tmax) * sizeof(c128));
+  chunk = std::max<size_t>(1, std::min(chunk, pairs.size()));
+  chunk = std::min<size_t>(chunk, (size_t)1 << 22);
+  c128 *E = nullptr, *T = nullptr; int2* pairs_dev = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaError_t e = pool_alloc_t(&E, chunk * emax * sizeof(c128));
+  if (e == cudaSuccess) e = pool_alloc_t(&T, chunk * tmax * sizeof(c128));
+  if (e == cudaSuccess) e = pool_alloc_t(&pairs_dev, pairs.size() * sizeof(int2));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(pairs_dev, pairs.data(), pairs.size() * sizeof(int2), cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = cudaEventCreate(&e0);
+  if (e == cudaSuccess) e = cudaEventCreate(&e1);
+  if (e == cudaSuccess) e = cudaEventRecord(e0, stream);
+  for (size_t p0 = 0; p0 < pairs.size() && e == cudaSuccess; p0 += chunk) {
+    const int cnt = (int)std::min(chunk, pairs.size() - p0);
+    e = qk_launch_gram_big(n, soff_x, soff_y, dims_x, dims_y, storeX, strideX, chiX, storeY, strideY, chiY,
+                           pairs_dev + p0, cnt, symmetric, E, emax, T, tmax, K_dev, ldk, stream);
+  }
+  if (e == cudaSuccess) e = cudaEventRecord(e1, stream);
+  if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+  float ms = 0.f;
+  if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  pool_free(E); pool_free(T); pool_free(pairs_dev);
+  if (e != cudaSuccess) return cuda_fail(e, "batched-GEMM Gram kernels");
+  if (ms_out) *ms_out = ms;
+  return QK_OK;
+}
+
+int qk_gram_big(const qk_plan* plan, int device, void* stream_v, const int32_t* dims_x, const int32_t* dims_y,
+                const void* storeX, const int32_t* chiX, int Nx, const void* storeY, const int32_t* chiY, int Ny,
+                const int32_t* tiles, int n_tiles, int symmetric, double* K_dev, int64_t ldk, float* ms_out) {
+  if (!plan || !storeX || !chiX || Nx < 1 || !K_dev || n_tiles < 0 || (n_tiles > 0 && !tiles))
+    return fail(QK_ERR_ARG, "bad arguments");
+  if (symmetric) { storeY = storeX; chiY = chiX; Ny = Nx; dims_y = dims_x; }
+  if (!storeY || !chiY || Ny < 1) return fail(QK_ERR_ARG, "bad Y arguments");
+  if (ldk < Nx) return fail(QK_ERR_ARG, "ldk must be >= Nx");
+  if (!dims_x) dims_x = plan->cap.data();
+  if (!dims_y) dims_y = plan->cap.data();
+  for (int b = 0; b <= plan->n; ++b)
+    if (dims_x[b] < 1 || dims_y[b] < 1 || dims_x[b] > plan->cap[b] || dims_y[b] > plan->cap[b])
+      return fail(QK_ERR_ARG, "per-bond maxima must lie in [1, bond cap of the plan]");
+  return gram_big_run(device, (cudaStream_t)stream_v, plan->n, plan->site_off.data(), plan->site_off.data(), dims_x, dims_y,
+                      (const c128*)storeX, plan->state_stride, chiX, Nx, (const c128*)storeY, plan->state_stride, chiY, Ny,
+                      tiles, n_tiles, symmetric, K_dev, ldk, ms_out);
+}
+
+int qk_batch_repack(const qk_batch* b, const qk_plan* plan, void* store_dev, int32_t* chi_dev, const int32_t* dst_index,
+                    void* stream_v) {
+  if (!b || !plan || !store_dev || !chi_dev) return fail(QK_ERR_ARG, "NULL argument");
+  if (b->n != plan->n) return fail(QK_ERR_ARG, "batch and plan differ in the number of qubits");
+  if (b->N == 0) return QK_OK;
+  QK_CUDA(cudaSetDevice(b->device), "cudaSetDevice");
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  int64_t* off_dev = nullptr; int32_t* dst_dev = nullptr;
+  QK_CUDA(pool_alloc_t(&off_dev, (b->n + 1) * sizeof(int64_t)), "cudaMalloc(offsets)");
+  cudaError_t e = cudaMemcpyAsync(off_dev, plan->site_off.data(), (b->n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess && dst_index) e = pool_alloc_t(&dst_dev, (size_t)b->N * sizeof(int32_t));
+  if (e == cudaSuccess && dst_index)
+    e = cudaMemcpyAsync(dst_dev, dst_index, (size_t)b->N * sizeof(int32_t), cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess)
+    e = qk_launch_repack(b->n, b->N, b->store, b->state_stride, b->site_off_dev, b->chi, (c128*)store_dev,
+                         plan->state_stride, off_dev, chi_dev, dst_dev, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  pool_free(off_dev); pool_free(dst_dev);
+  if (e != cudaSuccess) return cuda_fail(e, "repack kernel");
   return QK_OK;
 }
 

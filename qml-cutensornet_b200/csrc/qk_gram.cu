@@ -893,3 +893,181 @@ cudaError_t qk_run_pipe_mix(int iters, float* ms3) {
   cudaFree(sink);
   return e != cudaSuccess ? e : cudaGetLastError();
 }
+
+// ------------------------------------------------------------------------------------------------
+// Stage 2 for bond dimensions above the register-resident kernels (chi > 16; BASELINE config 4): the transfer
+// sweep of every (bra, ket) pair as two batched complex GEMMs per site on the FP64 tensor cores,
+//     step 1   T[a,(p,c')]  = sum_c      E[a,c]              A_x[c,(p,c')]      M = chi_y(l), K = chi_x(l), N = 2 chi_x(r)
+//     step 2   E'[b',c']    = sum_{(a,p)} conj(A_y[(a,p),b']) T[(a,p),c']        M = chi_y(r), K = 2 chi_y(l), N = chi_x(r)
+// with E and T of every pair of the launch in global memory (compact row-major, true bond dimensions) and the site
+// tensors read straight from the unpadded stage-1 stores ([chi_l][2][chi_r] is already the row-major K x N / K x M
+// operand).  At chi ~ 100 one site step of one pair is 32 chi^3 = 32 MFLOP against ~1.5 MB of operands: compute
+// bound.  CTA = 4 warps, tile 32 x 64, each warp 16 x 32 as 2 x 4 DMMA m8n8k4 tiles; complex product = 4 real MMAs
+// (no 3M here: the operand sums would need an extra pass over shared memory and the tiles are full at these sizes).
+// ------------------------------------------------------------------------------------------------
+struct BigGemmArgs {
+  const int2* pairs;          // (y, x) per pair of this launch
+  int nb;                     // n + 1
+  const int32_t* chiX;        // [Nx][nb]
+  const int32_t* chiY;
+  const c128* storeX;
+  const c128* storeY;
+  int64_t strideX, strideY;   // c128 per state
+  int64_t off_x, off_y;       // slot offset of this site inside a state, c128
+  c128* E;
+  c128* T;
+  int64_t e_stride, t_stride; // c128 per pair
+  int site;
+  int tiles_n, tpp;           // tiles along N, tiles per pair (maxima over the batch)
+};
+
+template <int STEP>
+__global__ void __launch_bounds__(128) qk_big_gemm_kernel(const __grid_constant__ BigGemmArgs a) {
+  const int pair = blockIdx.x / a.tpp, tile = blockIdx.x - pair * a.tpp;
+  const int tm = tile / a.tiles_n, tn = tile - tm * a.tiles_n;
+  const int2 yx = a.pairs[pair];
+  const int32_t* cx = a.chiX + (size_t)yx.y * a.nb + a.site;
+  const int32_t* cy = a.chiY + (size_t)yx.x * a.nb + a.site;
+  const int cxl = cx[0], cxr = cx[1], cyl = cy[0], cyr = cy[1];
+  int M, N, K, lda, ldb;
+  const c128 *A, *B;
+  c128* C;
+  if (STEP == 1) {
+    M = cyl; K = cxl; N = 2 * cxr; lda = K; ldb = N;
+    A = a.E + (size_t)pair * a.e_stride;
+    B = a.storeX + (size_t)yx.y * a.strideX + a.off_x;
+    C = a.T + (size_t)pair * a.t_stride;
+  } else {
+    M = cyr; K = 2 * cyl; N = cxr; lda = M; ldb = N;
+    A = a.storeY + (size_t)yx.x * a.strideY + a.off_y;
+    B = a.T + (size_t)pair * a.t_stride;
+    C = a.E + (size_t)pair * a.e_stride;
+  }
+  const int m0 = tm * 32, n0 = tn * 64;
+  if (m0 >= M || n0 >= N) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, j4 = lane & 3;
+  const int mw = m0 + (warp >> 1) * 16, nw = n0 + (warp & 1) * 32;
+  double cr[2][4][2], ci[2][4][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { cr[i][j][0] = cr[i][j][1] = 0.0; ci[i][j][0] = ci[i][j][1] = 0.0; }
+  if (mw < M && nw < N) {
+#pragma unroll 2
+    for (int k0 = 0; k0 < K; k0 += 4) {
+      const int kk = k0 + j4;
+      double ar[2], ai[2], an[2], br[4], bi[4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int row = mw + i * 8 + g;
+        double2 v = make_double2(0.0, 0.0);
+        if (row < M && kk < K) v = *(const double2*)(STEP == 1 ? A + (size_t)row * lda + kk : A + (size_t)kk * lda + row);
+        ar[i] = v.x;
+        ai[i] = STEP == 1 ? v.y : -v.y;    // step 2 uses conj(A_y)
+        an[i] = -ai[i];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = nw + j * 8 + g;
+        double2 v = make_double2(0.0, 0.0);
+        if (kk < K && col < N) v = *(const double2*)(B + (size_t)kk * ldb + col);
+        br[j] = v.x; bi[j] = v.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          qk_dmma(cr[i][j], ar[i], br[j]);
+          qk_dmma(ci[i][j], ar[i], bi[j]);
+          qk_dmma(cr[i][j], an[i], bi[j]);
+          qk_dmma(ci[i][j], ai[i], br[j]);
+        }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int row = mw + i * 8 + g;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = nw + j * 8 + 2 * j4;
+      if (row < M) {
+        if (col < N) *(double2*)(C + (size_t)row * N + col) = make_double2(cr[i][j][0], ci[i][j][0]);
+        if (col + 1 < N) *(double2*)(C + (size_t)row * N + col + 1) = make_double2(cr[i][j][1], ci[i][j][1]);
+      }
+    }
+  }
+}
+
+__global__ void qk_big_init_kernel(c128* E, int64_t e_stride, int n_pairs) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n_pairs) E[(size_t)p * e_stride] = cmake(1.0, 0.0);     // E_0 = [1]
+}
+
+__global__ void qk_big_finish_kernel(const c128* E, int64_t e_stride, const int2* pairs, int n_pairs, int symmetric,
+                                     double* K, int64_t ldk) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  const c128 v = E[(size_t)p * e_stride];
+  const double k = v.x * v.x + v.y * v.y;
+  const int2 yx = pairs[p];
+  K[(size_t)yx.x * ldk + yx.y] = k;
+  if (symmetric) K[(size_t)yx.y * ldk + yx.x] = k;
+}
+
+// One chunk of pairs through the whole sweep.  dims_x / dims_y: per-bond maxima of the bond dimensions (host).
+cudaError_t qk_launch_gram_big(int n, const int64_t* site_off_x, const int64_t* site_off_y, const int32_t* dims_x,
+                               const int32_t* dims_y, const c128* storeX, int64_t strideX, const int32_t* chiX,
+                               const c128* storeY, int64_t strideY, const int32_t* chiY, const int2* pairs_dev,
+                               int n_pairs, int symmetric, c128* E, int64_t e_stride, c128* T, int64_t t_stride,
+                               double* K, int64_t ldk, cudaStream_t stream) {
+  if (n_pairs <= 0) return cudaSuccess;
+  qk_big_init_kernel<<<(n_pairs + 255) / 256, 256, 0, stream>>>(E, e_stride, n_pairs);
+  BigGemmArgs a;
+  a.pairs = pairs_dev; a.nb = n + 1; a.chiX = chiX; a.chiY = chiY; a.storeX = storeX; a.storeY = storeY;
+  a.strideX = strideX; a.strideY = strideY; a.E = E; a.T = T; a.e_stride = e_stride; a.t_stride = t_stride;
+  for (int s = 0; s < n; ++s) {
+    a.site = s; a.off_x = site_off_x[s]; a.off_y = site_off_y[s];
+    a.tiles_n = (2 * dims_x[s + 1] + 63) / 64;
+    a.tpp = ((dims_y[s] + 31) / 32) * a.tiles_n;
+    qk_big_gemm_kernel<1><<<(unsigned)((size_t)n_pairs * a.tpp), 128, 0, stream>>>(a);
+    a.tiles_n = (dims_x[s + 1] + 63) / 64;
+    a.tpp = ((dims_y[s + 1] + 31) / 32) * a.tiles_n;
+    qk_big_gemm_kernel<2><<<(unsigned)((size_t)n_pairs * a.tpp), 128, 0, stream>>>(a);
+  }
+  qk_big_finish_kernel<<<(n_pairs + 255) / 256, 256, 0, stream>>>(E, e_stride, pairs_dev, n_pairs, symmetric, K, ldk);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// repack: states of one store layout -> another (different bond caps => different slot offsets); one CTA per
+// (site, state).  Merges batches simulated with different caps into the one buffer that is exchanged.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) qk_repack_kernel(int n, const c128* __restrict__ src, int64_t src_stride,
+                                                        const int64_t* __restrict__ src_off, const int32_t* __restrict__ src_chi,
+                                                        c128* __restrict__ dst, int64_t dst_stride,
+                                                        const int64_t* __restrict__ dst_off, int32_t* __restrict__ dst_chi,
+                                                        const int32_t* __restrict__ dst_index) {
+  const int s = blockIdx.x, i = blockIdx.y;
+  const int idst = dst_index ? dst_index[i] : i;
+  if (idst < 0) return;
+  const int32_t* chi = src_chi + (size_t)i * (n + 1);
+  int64_t len = (int64_t)chi[s] * 2 * chi[s + 1];
+  const int64_t capacity = dst_off[s + 1] - dst_off[s];
+  if (len > capacity) len = capacity;       // cannot happen when the destination caps cover the states (host contract)
+  const c128* a = src + (size_t)i * src_stride + src_off[s];
+  c128* b = dst + (size_t)idst * dst_stride + dst_off[s];
+  for (int64_t k = threadIdx.x; k < len; k += blockDim.x) b[k] = a[k];
+  if (s == 0)
+    for (int k = threadIdx.x; k <= n; k += blockDim.x) dst_chi[(size_t)idst * (n + 1) + k] = chi[k];
+}
+
+cudaError_t qk_launch_repack(int n, int N, const c128* src, int64_t src_stride, const int64_t* src_off_dev,
+                             const int32_t* src_chi, c128* dst, int64_t dst_stride, const int64_t* dst_off_dev,
+                             int32_t* dst_chi, const int32_t* dst_index_dev, cudaStream_t stream) {
+  if (N <= 0) return cudaSuccess;
+  dim3 grid(n, N);
+  qk_repack_kernel<<<grid, 128, 0, stream>>>(n, src, src_stride, src_off_dev, src_chi, dst, dst_stride, dst_off_dev,
+                                             dst_chi, dst_index_dev);
+  return cudaGetLastError();
+}

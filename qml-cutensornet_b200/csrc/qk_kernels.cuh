@@ -13,6 +13,10 @@ cudaError_t qk_launch_sim(const SimParams& P, int G, size_t smem_bytes, int* wor
 cudaError_t qk_launch_sim_b(const SimParams& P, int G, size_t smem_bytes, int ncta, QkStat* parts, cudaStream_t stream,
                             int* grid_out);
 
+// Large-matrix path (chi_cap > 32, qk_sim_big.h): ncta_req <= 0 picks the cluster size from the SM count and N.
+cudaError_t qk_sim_big_config(size_t smem_bytes, int N, int ncta_req, int* ncta_out, int* n_clusters_out);
+cudaError_t qk_launch_sim_big(const SimParams& P, size_t smem_bytes, int ncta, int n_clusters, cudaStream_t stream);
+
 // ---- exchange format ("frag") ----
 // Per state: for every site s a block of Dl*Dr*4 doubles in DMMA A-fragment order, then n+1 bytes
 // (padded to 16) holding ceil(chi_b / 8) per bond.  See DESIGN.md "Data layout".
@@ -74,6 +78,17 @@ struct LaneParams {
 };
 cudaError_t qk_launch_gram_lane(const LaneParams& P, int dm /* 2 or 4 */, cudaStream_t stream);
 void qk_gram_lane_tile_shape(int* tx, int* ty);
+
+// Batched-GEMM overlap sweep on the unpadded stores for any bond dimension (qk_gram.cu): one chunk of pairs.
+cudaError_t qk_launch_gram_big(int n, const int64_t* site_off_x, const int64_t* site_off_y, const int32_t* dims_x,
+                               const int32_t* dims_y, const c128* storeX, int64_t strideX, const int32_t* chiX,
+                               const c128* storeY, int64_t strideY, const int32_t* chiY, const int2* pairs_dev,
+                               int n_pairs, int symmetric, c128* E, int64_t e_stride, c128* T, int64_t t_stride,
+                               double* K, int64_t ldk, cudaStream_t stream);
+
+cudaError_t qk_launch_repack(int n, int N, const c128* src, int64_t src_stride, const int64_t* src_off_dev,
+                             const int32_t* src_chi, c128* dst, int64_t dst_stride, const int64_t* dst_off_dev,
+                             int32_t* dst_chi, const int32_t* dst_index_dev, cudaStream_t stream);
 
 // CUDA-core cross-check on the unpadded stores
 cudaError_t qk_launch_gram_store(int n, const c128* storeX, int64_t strideX, const int64_t* site_off_x,

@@ -9,7 +9,7 @@
 // the absorb direction by looking ahead to the next 2-qubit gate; this removes gauge moves without
 // changing any singular value the truncation rule sees.
 #include "qk_plan.h"
-#include "qk_sim_core.h"
+#include "qk_sim_big.h"
 #include <math.h>
 #include <stdlib.h>
 #include <algorithm>
@@ -159,7 +159,9 @@ int qk_compile_plan(int n, const qk_gate* gates_in, int n_gates, int trunc_mode,
   plan->reorder = (flags & QK_PLAN_LITERAL_ORDER) ? 0 : 1;
   plan->early_exit = (flags & QK_PLAN_EARLY_EXIT) ? 1 : 0;
   plan->fuse = (flags & QK_PLAN_NO_FUSION) ? 0 : 1;
-  plan->parallel = (flags & QK_PLAN_PARALLEL) ? 1 : 0;
+  plan->big = (chi_cap > QK_CHI_LIMIT || (flags & QK_PLAN_BIG)) ? 1 : 0;
+  // (the large-matrix kernel already spreads one datapoint over a cluster: no B form there)
+  plan->parallel = ((flags & QK_PLAN_PARALLEL) && !plan->big) ? 1 : 0;
   if (plan->parallel) plan->reorder = 0;   // the literal order has the shallow dependency graph (C3: depth 28)
   plan->level_start.clear();
   if (n < 1) { *err = "n_qubits must be >= 1"; return QK_ERR_ARG; }
@@ -167,8 +169,8 @@ int qk_compile_plan(int n, const qk_gate* gates_in, int n_gates, int trunc_mode,
   if (trunc_mode != QK_TRUNC_ITENSORS && trunc_mode != QK_TRUNC_PYTKET) { *err = "bad truncation mode"; return QK_ERR_ARG; }
   if (!(trunc_error >= 0.0) || trunc_error >= 1.0) { *err = "truncation_error must be in [0, 1)"; return QK_ERR_ARG; }
   if (chi_cap < 1) { *err = "chi_cap must be >= 1"; return QK_ERR_ARG; }
-  if (chi_cap > QK_CHI_LIMIT) {
-    *err = "bond dimension cap above the shared-memory-resident limit (chi <= 32)";
+  if (chi_cap > QK_CHI_LIMIT_BIG) {
+    *err = "bond dimension cap above the limit of the stage-1 kernels (chi <= 256)";
     return QK_ERR_LIMIT;
   }
   plan->n = n; plan->n_gates = n_gates; plan->trunc_mode = trunc_mode; plan->trunc_error = trunc_error;
@@ -310,5 +312,18 @@ int qk_compile_plan(int n, const qk_gate* gates_in, int n_gates, int trunc_mode,
   plan->rmax = 2 * capmax;
   plan->threads = qk_pick_threads(capmax);
   plan->smem_bytes = qk_sim_smem_bytes(n, plan->rmax, plan->threads);
+  if (plan->big) {
+    // gauge moves become SVDs of the site pair with an identity gate and no truncation: MOVE_R of site s pushes the
+    // centre to s + 1 (bond (s, s+1), singular values to the right), MOVE_L of site s to s - 1 (bond (s-1, s), left)
+    for (QkOp& op : plan->ops) {
+      if (op.kind == QK_OP_MOVE_R) { op.kind = QK_OP_ID2; op.dir = QK_DIR_RIGHT; op.pad = QK_OPF_NOTRUNC; }
+      else if (op.kind == QK_OP_MOVE_L) { op.kind = QK_OP_ID2; op.site -= 1; op.dir = QK_DIR_LEFT; op.pad = QK_OPF_NOTRUNC; }
+    }
+    plan->threads = 256;
+    plan->jb = 8;
+    if (const char* e = getenv("QK_BIG_JB")) { const int v = atoi(e); if (v >= 1 && v <= 16) plan->jb = v; }   // tests
+    while (plan->jb > 1 && (size_t)plan->rmax * 2 * plan->jb * sizeof(c128) > (size_t)144 * 1024) plan->jb /= 2;
+    plan->smem_bytes = qk_big_smem_bytes(n, plan->rmax, plan->jb, plan->threads);
+  }
   return QK_OK;
 }

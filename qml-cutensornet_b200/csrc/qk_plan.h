@@ -24,6 +24,8 @@ struct qk_plan {
   int fuse = 1;                    // fuse consecutive 2-qubit gates on one bond (off: QK_PLAN_NO_FUSION)
   int parallel = 0;                // QK_PLAN_PARALLEL: B form, levelised ops
   std::vector<int32_t> level_start;  // [n_levels + 1] (parallel plans)
+  int big = 0;                     // large-matrix path (qk_sim_big.h): chi_cap above QK_CHI_LIMIT, or QK_PLAN_BIG
+  int jb = 8;                      // columns per block of its block Jacobi
 };
 
 // Returns 0 or a negative qk_status; err receives a message.
@@ -33,4 +35,5 @@ int qk_compile_plan(int n_qubits, const qk_gate* gates, int n_gates, int trunc_m
 int qk_ansatz_gates(int n_qubits, int reps, double gamma, int hadamard_init, const int32_t* pairs, int n_pairs,
                     std::vector<qk_gate>* out, std::string* err);
 int qk_pick_threads(int chi_cap);
-#define QK_CHI_LIMIT 32
+#define QK_CHI_LIMIT 32        // shared-memory-resident stage-1 kernels (qk_sim_core.h)
+#define QK_CHI_LIMIT_BIG 256   // large-matrix stage-1 kernel (qk_sim_big.h)

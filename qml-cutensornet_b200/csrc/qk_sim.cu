@@ -12,7 +12,10 @@
 #include "qk_kernels.cuh"
 // level barrier of the B-form path: the CTAs of one thread-block cluster share a datapoint
 #define QK_GROUP_SYNC() do { __threadfence(); cooperative_groups::this_cluster().sync(); __threadfence(); } while (0)
-#include "qk_sim_core.h"
+// cluster barrier of the large-matrix path (fences on both sides: global data written by one CTA is read by others)
+#define QK_CSYNC(c) do { if ((c).ncta > 1) { __threadfence(); cooperative_groups::this_cluster().sync(); __threadfence(); } \
+                         else __syncthreads(); } while (0)
+#include "qk_sim_big.h"
 
 // resident CTAs per SM the register allocation is sized for (shared memory allows 6 at chi_cap 16)
 template <int G> struct SimMinBlocks { static constexpr int value = (G == 128) ? 6 : (G == 64) ? 8 : (G == 32) ? 12 : 2; };
@@ -116,4 +119,74 @@ cudaError_t qk_launch_sim_b(const SimParams& P, int G, size_t smem_bytes, int nc
     case 256: return launch_b<256>(P, smem_bytes, ncta, parts, stream, grid_out);
     default: return cudaErrorInvalidValue;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Large-matrix kernel (qk_sim_big.h): one cluster of `ncta` CTAs x 256 threads per datapoint, persistent clusters.
+// ------------------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(G, 1) qk_sim_big_kernel(const __grid_constant__ SimParams P) {
+  extern __shared__ __align__(16) unsigned char qk_smem[];
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int ncta = (int)cluster.num_blocks();
+  const int cta = (int)cluster.block_rank();
+  const int n_clusters = (int)(gridDim.x / ncta);
+  const int slot = (int)(blockIdx.x / ncta);
+  SimCtx c;
+  qk_big_carve(c, &P, qk_smem, G, slot, cta, ncta);
+  for (int dp = slot; dp < P.N; dp += n_clusters) {
+    const long long t0 = clock64();
+    qk_big_datapoint<G>(c, dp);
+    if (P.unit_clk && cta == 0 && threadIdx.x == 0) P.unit_clk[dp] = clock64() - t0;
+  }
+}
+
+static cudaError_t big_cfg(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, size_t smem, int ncta, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(qk_sim_big_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (ncta > 8) {
+    e = cudaFuncSetAttribute(qk_sim_big_kernel<256>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+  }
+  *cfg = cudaLaunchConfig_t{};
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)ncta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg->blockDim = dim3(256); cfg->dynamicSmemBytes = smem; cfg->stream = stream; cfg->attrs = attr; cfg->numAttrs = 1;
+  cfg->gridDim = dim3((unsigned)ncta);
+  return cudaSuccess;
+}
+
+cudaError_t qk_sim_big_config(size_t smem_bytes, int N, int ncta_req, int* ncta_out, int* n_clusters_out) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int ncta = ncta_req;
+  if (ncta <= 0) {   // as many CTAs per datapoint as the SMs allow: 148 SMs / N datapoints, a power of two <= 16
+    ncta = 1;
+    while (ncta * 2 <= 16 && ncta * 2 * (N < 1 ? 1 : N) <= sms) ncta *= 2;
+  }
+  cudaError_t e = cudaSuccess;
+  for (; ncta >= 1; ncta /= 2) {
+    cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+    e = big_cfg(&cfg, attr, smem_bytes, ncta, nullptr);
+    int max_clusters = 0;
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&max_clusters, qk_sim_big_kernel<256>, &cfg);
+    if (e == cudaSuccess && max_clusters >= 1) {
+      *ncta_out = ncta;
+      *n_clusters_out = max_clusters < N ? max_clusters : (N < 1 ? 1 : N);
+      return cudaSuccess;
+    }
+    cudaGetLastError();
+    if (ncta == 1) break;
+  }
+  return e != cudaSuccess ? e : cudaErrorInvalidConfiguration;
+}
+
+cudaError_t qk_launch_sim_big(const SimParams& P, size_t smem_bytes, int ncta, int n_clusters, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+  cudaError_t e = big_cfg(&cfg, attr, smem_bytes, ncta, stream);
+  if (e != cudaSuccess) return e;
+  cfg.gridDim = dim3((unsigned)(n_clusters * ncta));
+  return cudaLaunchKernelEx(&cfg, qk_sim_big_kernel<256>, P);
 }

@@ -72,6 +72,11 @@ struct SimCtx {
   SimShared* sh;
   c128* state;    // global: this datapoint's site slots
   double* lam;    // global: this datapoint's bond weights [(n+1)][lam_ld] (B form only)
+  // large-matrix path (qk_sim_big.h): W above points to global memory
+  c128* Wb;       // shared: one pair of column blocks of W (rmax x 2 jb)
+  c128* S;        // global: staging of the recovered factor
+  int* gflag;     // global: [3] rotating "a rotation happened" flags of the cluster
+  int cta, ncta;  // rank / size of the CTA group that shares the datapoint
 };
 
 // bytes of shared memory the core needs for group size G
@@ -154,6 +159,10 @@ QK_DEV void qk_build_gate_2q(const QkOp& op, const double* x, c128* g) {
   for (int i = 0; i < 16; ++i) g[i] = cmake(0, 0);
   if (op.kind == QK_OP_SWAP) {
     g[0 * 4 + 0] = g[1 * 4 + 2] = g[2 * 4 + 1] = g[3 * 4 + 3] = cmake(1, 0);
+    return;
+  }
+  if (op.kind == QK_OP_ID2) {
+    g[0] = g[5] = g[10] = g[15] = cmake(1, 0);
     return;
   }
   const double th = qk_angle(op, x);

@@ -26,7 +26,8 @@ QK_PLAN_LITERAL_ORDER = 1
 QK_PLAN_EARLY_EXIT = 2
 QK_PLAN_NO_FUSION = 4
 QK_PLAN_PARALLEL = 8
-CHI_LIMIT = 32          # shared-memory-resident stage-1 kernel
+CHI_LIMIT = 256         # stage-1 kernels: shared-memory-resident up to 32, large-matrix (cluster) kernel above
+QK_PLAN_BIG = 16
 DMMA_D_LIMIT = 16       # register-resident tensor-core overlap kernel
 
 GATE_KIND = {"H": 0, "Rz": 1, "Rx": 2, "XXPhase": 3, "ZZPhase": 4, "SWAP": 5}
@@ -61,7 +62,7 @@ EXPORTS = [
     "qk_simulate", "qk_simulate_dev", "qk_simulate_trace", "qk_batch_sim_ms", "qk_batch_size", "qk_batch_info", "qk_batch_export",
     "qk_batch_import", "qk_batch_max_chi", "qk_batch_destroy", "qk_frag_stride", "qk_batch_pack",
     "qk_batch_pack_scatter",
-    "qk_gram_frags", "qk_batch_store", "qk_gram_lane", "qk_gram_store", "qk_gram_host", "qk_dmma_peak", "qk_pipe_mix",
+    "qk_gram_frags", "qk_batch_store", "qk_gram_lane", "qk_gram_store", "qk_gram_host", "qk_dmma_peak", "qk_pipe_mix", "qk_gram_big", "qk_batch_repack",
 ]
 
 _lib = None
@@ -235,6 +236,15 @@ class Batch:
         _check(lib().qk_batch_pack_scatter(self._h, _p(D, ctypes.c_int32), ctypes.c_void_p(frag_ptr),
                                            _p(dst, ctypes.c_int32), ctypes.c_void_p(stream)))
 
+    def repack(self, plan, store_ptr: int, chi_ptr: int, dst_index=None, stream: int = 0):
+        """Copy the states into a store laid out for ``plan`` (state i -> position dst_index[i], negative: skip)."""
+        dst = None
+        if dst_index is not None:
+            dst = np.ascontiguousarray(dst_index, dtype=np.int32)
+            assert dst.shape == (self.N,)
+        _check(lib().qk_batch_repack(self._h, plan._h, ctypes.c_void_p(store_ptr), ctypes.c_void_p(chi_ptr),
+                                     None if dst is None else _p(dst, ctypes.c_int32), ctypes.c_void_p(stream)))
+
     def store(self):
         """(device pointer of the unpadded store, c128 per state, device pointer of chi [N][n+1] int32)."""
         ptr, chi, stride = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64()
@@ -340,6 +350,21 @@ def gram_lane(plan: Plan, device, max_chi, storex_ptr, chix_ptr, Nx, storey_ptr,
                               ctypes.c_void_p(chix_ptr), int(Nx), ctypes.c_void_p(storey_ptr or 0),
                               ctypes.c_void_p(chiy_ptr or 0), int(Ny), _p(tiles, ctypes.c_int32), int(tiles.shape[0]),
                               int(bool(symmetric)), ctypes.c_void_p(k_ptr), ctypes.c_int64(ldk), ctypes.byref(ms)))
+    return ms.value
+
+
+def gram_big(plan: Plan, device, dims_x, dims_y, storex_ptr, chix_ptr, Nx, storey_ptr, chiy_ptr, Ny, tiles, symmetric, k_ptr,
+             ldk, stream=0) -> float:
+    """Batched-GEMM overlap sweep on the unpadded stores (any bond dimension within the plan's caps)."""
+    tiles = np.ascontiguousarray(np.asarray(tiles, dtype=np.int32).reshape(-1, 4))
+    dx = np.ascontiguousarray(dims_x, dtype=np.int32)
+    dy = dx if dims_y is None else np.ascontiguousarray(dims_y, dtype=np.int32)
+    ms = ctypes.c_float()
+    _check(lib().qk_gram_big(plan._h, int(device), ctypes.c_void_p(stream), _p(dx, ctypes.c_int32), _p(dy, ctypes.c_int32),
+                             ctypes.c_void_p(storex_ptr), ctypes.c_void_p(chix_ptr), int(Nx),
+                             ctypes.c_void_p(storey_ptr or 0), ctypes.c_void_p(chiy_ptr or 0), int(Ny),
+                             _p(tiles, ctypes.c_int32), int(tiles.shape[0]), int(bool(symmetric)), ctypes.c_void_p(k_ptr),
+                             ctypes.c_int64(ldk), ctypes.byref(ms)))
     return ms.value
 
 

@@ -22,7 +22,7 @@ import numpy as np
 import os
 
 from . import (CHI_LIMIT, DMMA_D_LIMIT, QK_FLAG_CAP_HIT, QK_FLAG_NO_CONVERGE, QkError, frag_stride,
-               gram_frags, gram_lane, pad_dims, simulate_dev)
+               gram_big, gram_frags, gram_lane, pad_dims, simulate_dev)
 
 PARALLEL_MAX_LOCAL = 150   # datapoints per GPU up to which stage 1 uses one CTA cluster per datapoint
 LANE_CHI_LIMIT = 4   # at or below this bond dimension stage 2 runs one lane per pair on the FP64 CUDA cores
@@ -88,7 +88,11 @@ def _torch():
     return torch
 
 
-CAP_LADDER = (4, 8, 16, 24, 32)   # bond caps tried in turn; each has its own kernel configuration
+# bond caps tried in turn; each has its own kernel configuration: <= 32 shared-memory-resident kernels (one CTA or, in
+# B form, one small cluster per datapoint), above that the large-matrix kernel (theta in L2, block Jacobi, one CTA
+# cluster per datapoint -- BASELINE config 4)
+CAP_LADDER = (4, 8, 16, 24, 32, 64, 128, 256)
+FRAG_D_LIMIT = 32    # padded bond dimension up to which stage 2 runs on the packed-fragment kernels
 
 
 class ShardStates:
@@ -162,7 +166,7 @@ def _simulate_shard(plan_factory, X_shard, device, chi_cap, comm, n_qubits, esca
     states = ShardStates(n_local, n_qubits)
     ladder = [c for c in CAP_LADDER if c >= chi_cap]
     if not ladder:
-        raise QkError(-3, f"bond dimension cap {chi_cap} above the shared-memory-resident limit (chi <= {CHI_LIMIT})")
+        raise QkError(-3, f"bond dimension cap {chi_cap} above the limit of the stage-1 kernels (chi <= {CHI_LIMIT})")
     stream = torch.cuda.current_stream().cuda_stream
 
     # Small shards (the multi-GPU regime: 125 datapoints per GPU at 8 GPUs) are bound by the latency of ONE
@@ -195,8 +199,7 @@ def _simulate_shard(plan_factory, X_shard, device, chi_cap, comm, n_qubits, esca
         states.cap = max(states.cap, cap)
         pending = run(cap, pending, not last)
         if last and len(pending):
-            raise QkError(-3, f"bond dimension exceeds the shared-memory-resident limit (chi <= {CHI_LIMIT}); "
-                              "the large-chi stage-1 path is not implemented")
+            raise QkError(-3, f"bond dimension exceeds the limit of the stage-1 kernels (chi <= {CHI_LIMIT})")
         level += 1
     if n_local == 0:
         states.plan = plan_factory(ladder[0], False)
@@ -268,13 +271,15 @@ def build_gram(comm, plan_factory, n_qubits, X, Y=None, chi_cap=16, device=None,
     if not symmetric:
         lane_local = lane_local and (sy.single_batch() is not None or sy.n_local == 0) and \
             (sx.n_local == 0 or sy.n_local == 0 or sy.cap == sx.cap)
-    flag = np.array([0 if lane_local else 1], dtype=np.int32)
+    flag = np.array([0 if lane_local else 1, max(sx.cap, sy.cap if sy is not None else 1)], dtype=np.int32)
     red = allreduce_max_array(comm, np.concatenate([sx.max_chi(), sy.max_chi() if not symmetric else sx.max_chi(), flag]))
     nb = n_qubits + 1
     Dx = pad_dims(red[:nb])
     Dy = Dx if symmetric else pad_dims(red[nb:2 * nb])
     max_chi = int(red[:2 * nb].max())
-    use_lane = (max_chi <= LANE_CHI_LIMIT and int(red[-1]) == 0 and os.environ.get("QK_GRAM_LANE", "1") != "0")
+    cap_common = int(red[-1])
+    use_lane = (max_chi <= LANE_CHI_LIMIT and int(red[-2]) == 0 and os.environ.get("QK_GRAM_LANE", "1") != "0")
+    use_big = (not use_lane) and (int(max(Dx.max(), Dy.max())) > FRAG_D_LIMIT or os.environ.get("QK_GRAM_BIG", "0") == "1")
     stream = torch.cuda.current_stream().cuda_stream
     K = torch.zeros((Ny, Nx), dtype=torch.float64, device=dev)
     tiles = row_tiles(Ny, Nx, symmetric, size, rank)
@@ -311,6 +316,39 @@ def build_gram(comm, plan_factory, n_qubits, X, Y=None, chi_cap=16, device=None,
                            tiles, symmetric, K.data_ptr(), Nx, stream)
             launches += 1
         del keep_x, keep_y
+    elif use_big:
+        # bond dimensions above the fragment kernels (BASELINE config 4): every rank re-lays its states out for the
+        # common bond cap, the unpadded stores + bond dimensions are exchanged, and the transfer sweep runs as
+        # batched complex GEMMs on the FP64 tensor cores
+        prof["gram_kernel"] = "qk_big_gemm_kernel"
+        plan = plan_factory(cap_common, False)
+        stride_b = int(plan.info().state_stride) * 16
+
+        def relaid(shard, n_total):
+            per = -(-n_total // size)
+            st = torch.empty(max(per, 1) * stride_b, dtype=torch.uint8, device=dev)
+            ch = torch.ones(max(per, 1) * nb, dtype=torch.int32, device=dev)
+            for batch, _, ok, pos in shard.parts:
+                if len(ok):
+                    dst = np.full(batch.N, -1, dtype=np.int32)
+                    dst[ok] = pos
+                    batch.repack(plan, st.data_ptr(), ch.data_ptr(), dst, stream)
+                    shard.launches += 1
+            if size == 1:
+                return st, ch
+            return allgather_bytes(comm, st), allgather_bytes(comm, ch)
+
+        stx, chx = relaid(sx, Nx)
+        sty, chy = (stx, chx) if symmetric else relaid(sy, Ny)
+        torch.cuda.synchronize()
+        prof["exchange_s"] = time.perf_counter() - t0
+        prof["frag_bytes_per_state"] = (stride_b, stride_b)
+        if tiles:
+            ms = gram_big(plan, device, red[:nb], None if symmetric else red[nb:2 * nb], stx.data_ptr(), chx.data_ptr(), Nx,
+                          None if symmetric else sty.data_ptr(), None if symmetric else chy.data_ptr(), Ny, tiles,
+                          symmetric, K.data_ptr(), Nx, stream)
+            launches += 2 * n_qubits + 2
+        del stx, chx, sty, chy
     else:
         prof["gram_kernel"] = "qk_gram_dmma_kernel" if int(max(Dx.max(), Dy.max())) <= DMMA_D_LIMIT else \
             "qk_gram_frag_generic_kernel"   # D > 16: CUDA-core kernel on the same packed buffers (any rank count)

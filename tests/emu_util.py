@@ -41,7 +41,7 @@ def gates_to_c(gates):
 def build_emu() -> ctypes.CDLL:
     so = EMU_DIR / "libqk_emu.so"
     srcs = [EMU_DIR / "qk_emu.cpp", CSRC / "qk_plan.cpp"]
-    deps = srcs + [CSRC / "qk_sim_core.h", CSRC / "qk_types.h", CSRC / "qk_plan.h"]
+    deps = srcs + [CSRC / "qk_sim_core.h", CSRC / "qk_sim_big.h", CSRC / "qk_types.h", CSRC / "qk_plan.h"]
     if not so.exists() or any(d.stat().st_mtime > so.stat().st_mtime for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", str(so)] + [str(s) for s in srcs])
     lib = ctypes.CDLL(str(so))

@@ -11,11 +11,16 @@
 #include <string>
 #include <vector>
 #include "../../qml-cutensornet_b200/csrc/qk_plan.h"
-#include "../../qml-cutensornet_b200/csrc/qk_sim_core.h"
+#include "../../qml-cutensornet_b200/csrc/qk_sim_big.h"
 
 template <int G>
 static void run_group(const SimParams& P, unsigned char* smem, int dp) {
   SimCtx c;
+  if (P.big_w) {   // large-matrix path: one CTA stands for the whole cluster
+    qk_big_carve(c, &P, smem, G, 0, 0, 1);
+    qk_big_datapoint<G>(c, dp);
+    return;
+  }
   qk_sim_carve(c, &P, smem, G);
   if (P.parallel) {
     QkStat part;
@@ -61,7 +66,16 @@ long long qk_emu_simulate(int n, const qk_gate* gates, int n_gates, int trunc_mo
     P.level_start = plan.level_start.data();
     P.n_levels = (int)plan.level_start.size() - 1;
   }
-  size_t bytes = qk_sim_smem_bytes(n, plan.rmax, G);
+  std::vector<c128> big_w, big_s;
+  std::vector<int> big_flag(4, 0);
+  P.big_w = nullptr; P.big_s = nullptr; P.big_w_stride = P.big_s_stride = 0; P.big_flag = nullptr; P.big_jb = plan.jb;
+  P.unit_clk = nullptr;
+  if (plan.big) {
+    big_w.resize((size_t)plan.rmax * plan.rmax);
+    big_s.resize((size_t)plan.rmax * plan.rmax / 2);
+    P.big_w = big_w.data(); P.big_s = big_s.data(); P.big_flag = big_flag.data();
+  }
+  size_t bytes = plan.big ? qk_big_smem_bytes(n, plan.rmax, plan.jb, G) : qk_sim_smem_bytes(n, plan.rmax, G);
   unsigned char* smem = (unsigned char*)aligned_alloc(64, (bytes + 63) & ~(size_t)63);
   for (int dp = 0; dp < N; ++dp) {
     memset(smem, 0xA5, bytes);   // poison: the core must not depend on stale shared memory

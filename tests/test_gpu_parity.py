@@ -555,3 +555,81 @@ def test_gamma_zero_and_zero_cutoff(qk, cuda_device):
     ans = KernelStateAnsatz(n, 2, 0.9, emap)
     K = bkm_cpu(SingleComm(), ans, X, info_file="/tmp/qk_zero", truncation_error=0.0)
     assert np.abs(K - oracle.statevector_gram(n, 2, 0.9, emap, X)).max() < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: bond dimensions above 32 (BASELINE config 4) -- large-matrix stage 1, batched-GEMM stage 2
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cluster,jb", [(1, 8), (2, 4), (4, 2), (8, 8), (16, 8)])
+def test_large_matrix_kernel_forced_on_small_caps(qk, cuda_device, monkeypatch, cluster, jb):
+    """QK_PLAN_BIG runs the large-matrix stage-1 kernel (theta in global memory, block Jacobi over column blocks of
+    jb, one cluster of `cluster` CTAs per datapoint) on a problem the shared-memory kernel also solves: same bond
+    dimensions as the oracle on every bond (ITensors rule, oracle gate order, gauge moves as identity-gate SVDs),
+    Gram within 1e-12 of the shared-memory kernel and within 1e-8 of the exact statevector."""
+    monkeypatch.setenv("QK_BIG_CLUSTER", str(cluster))
+    monkeypatch.setenv("QK_BIG_JB", str(jb))
+    n, r, g, d, cap, N = 12, 2, 0.7, 3, 32, 5
+    emap = oracle.entanglement_graph(n, d)
+    X = oracle.synthetic_features(N, n, 0)
+    ans = _ansatz(n, r, g, d)
+    ref = simulate_batch(n, r, g, emap, X)
+    Ksv = oracle.statevector_gram(n, r, g, emap, X)
+    b_lit = qk.simulate(_plan(qk, ans, 0, cap, flags=qk.QK_PLAN_BIG | qk.QK_PLAN_LITERAL_ORDER), X)
+    info = b_lit.info()
+    assert not np.any(info["flags"])
+    assert np.array_equal(info["chi"], np.array([[1] + m.bond_dims() + [1] for m in ref]))
+    K_lit, _ = b_lit.gram_store()
+    assert np.abs(K_lit - gram_from_mps(ref)).max() < 1e-11
+    b_big = qk.simulate(_plan(qk, ans, 0, cap, flags=qk.QK_PLAN_BIG), X)
+    b_small = qk.simulate(_plan(qk, ans, 0, cap), X)
+    assert not np.any(b_big.info()["flags"])
+    K_big, _ = b_big.gram_store()
+    K_small, _ = b_small.gram_store()
+    assert np.abs(K_big - K_small).max() < 1e-12
+    assert np.abs(K_big - Ksv).max() < TOL
+    b_pt = qk.simulate(_plan(qk, ans, 1, cap, flags=qk.QK_PLAN_BIG), X)      # pytket rule: renormalised, fidelity tracked
+    K_pt, _ = b_pt.gram_store()
+    assert np.abs(K_pt - Ksv).max() < TOL and np.abs(np.diag(K_pt) - 1).max() < 1e-12
+
+
+def test_batched_gemm_overlap_on_oracle_states(qk, cuda_device):
+    """Stage 2 for chi > 16 alone: oracle-made MPS with ragged bond dimensions up to 64 uploaded; the batched-GEMM
+    sweep (through qk_gram_store, which takes it above chi 32) against the oracle's sweep, square and rectangular."""
+    n, r, g, d = 14, 3, 0.8, 4
+    emap = oracle.entanglement_graph(n, d)
+    X = oracle.synthetic_features(7, n, 3)
+    Y = oracle.synthetic_features(4, n, 5)
+    rx = simulate_batch(n, r, g, emap, X)
+    ry = simulate_batch(n, r, g, emap, Y)
+    assert max(m.max_chi() for m in rx) > 32
+    bx = qk.import_batch([m.tensors for m in rx])
+    by = qk.import_batch([m.tensors for m in ry])
+    K, _ = bx.gram_store()
+    assert np.abs(K - gram_from_mps(rx)).max() < 1e-12
+    Kt, _ = bx.gram_store(by)
+    assert Kt.shape == (4, 7) and np.abs(Kt - gram_from_mps(rx, ry)).max() < 1e-12
+
+
+@pytest.mark.parametrize("backend", ["cpu", "gpu"])
+def test_high_bond_dimension_against_statevector(qk, cuda_device, backend):
+    """BASELINE config 4 regime at a qubit count the exact statevector still covers: 14 qubits, 4 layers, distance 4,
+    gamma = 1.0 -> bond dimensions up to the chain-centre bound 128.  Cap escalation 16 -> ... -> 128, large-matrix
+    stage 1, batched-GEMM stage 2, through both reference-facing entry points; Gram within 1e-8 of the exact
+    statevector (train and rectangular test x train)."""
+    import importlib
+    mod = importlib.import_module(f"{backend}_backend.kernel_state_ansatz")
+    from qkmps.engine import SingleComm
+    n, r, g, d = 14, 4, 1.0, 4
+    emap = oracle.entanglement_graph(n, d)
+    X = oracle.synthetic_features(6, n, 0)
+    Y = oracle.synthetic_features(3, n, 1)
+    ans = mod.KernelStateAnsatz(n, r, g, emap)
+    kw = dict(info_file="/tmp/qk_hi") if backend == "cpu" else {}
+    K = mod.build_kernel_matrix(SingleComm(), ans, X, truncation_error=1e-16, **kw)
+    prof = mod.build_kernel_matrix.last_profile
+    assert prof["info_x"]["chi"].max() > 64 and prof["gram_kernel"] == "qk_big_gemm_kernel"
+    assert np.abs(K - oracle.statevector_gram(n, r, g, emap, X)).max() < TOL
+    assert np.array_equal(K, K.T)
+    Kt = mod.build_kernel_matrix(SingleComm(), ans, X, Y, truncation_error=1e-16, **kw)
+    assert np.abs(Kt - oracle.statevector_gram(n, r, g, emap, X, Y)).max() < TOL
+    assert int(prof["info_x"]["chi"].max()) <= 128          # chain-centre bound 2^7
