@@ -168,3 +168,27 @@ def test_emu_parallel_b_form(emu, n, r, g, d, cap, mode):
             M = A.reshape(A.shape[0], -1)
             dev = np.abs(M @ M.conj().T - np.eye(M.shape[0]))
             assert dev.max() < 1e-3 and dev[0, 0] < 1e-12
+
+
+@pytest.mark.parametrize("jb", ["2", "8"])
+@pytest.mark.parametrize("n,r,g,d,cap", [(10, 2, 1.0, 2, 16), (10, 3, 0.9, 4, 32)])
+def test_emu_large_matrix_path(emu, monkeypatch, jb, n, r, g, d, cap):
+    """The large-matrix stage-1 core (qk_sim_big.h: theta in global memory, block Jacobi over column blocks, gauge
+    moves as identity-gate SVDs) through the host emulation, forced onto small caps with QK_PLAN_BIG (16): bond
+    dimensions identical to the oracle in its gate order, Gram within 1e-11 of the oracle and 1e-8 of the exact
+    statevector; the reordered + fused default schedule as well."""
+    monkeypatch.setenv("QK_BIG_JB", jb)
+    X = oracle.synthetic_features(3, n, 0)
+    emap = oracle.entanglement_graph(n, d)
+    gates = oracle.ansatz_gate_list(n, r, g, emap)
+    ref = simulate_batch(n, r, g, emap, X)
+    Kref = gram_from_mps(ref)
+    states, chi, stats, _ = emu_simulate(emu, n, gates, X, trunc_mode=0, chi_cap=cap, flags=16 | 1, threads=256)
+    assert np.array_equal(chi, np.array([[1] + m.bond_dims() + [1] for m in ref]))
+    assert not stats[:, 2].any()
+    assert np.abs(gram_from_mps([TensorsMPS(s) for s in states]) - Kref).max() < 1e-11
+    states, chi, stats, _ = emu_simulate(emu, n, gates, X, trunc_mode=0, chi_cap=cap, flags=16, threads=256)
+    K = gram_from_mps([TensorsMPS(s) for s in states])
+    assert not stats[:, 2].any()
+    assert np.abs(K - Kref).max() < 1e-9
+    assert np.abs(K - oracle.statevector_gram(n, r, g, emap, X)).max() < 1e-8
