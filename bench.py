@@ -407,6 +407,8 @@ def run_ours(args):
         return plans[key]
 
     cap0 = args.chi if args.chi > 0 else _initial_cap(ans, TRUNC_ERROR)
+    from qkmps.ansatz import structural_chi_bound
+    structural = cap0 >= max(1, structural_chi_bound(n, r, ans.entanglement_map))
     X_dev = torch.from_numpy(X).to(f"cuda:{device}")
     Y_dev = torch.from_numpy(Y).to(f"cuda:{device}") if M else None
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=f"cuda:{device}")
@@ -418,7 +420,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def step_device():
-        return build_gram(comm, plan_factory, n, X_dev, Y_dev, chi_cap=cap0, device=device, return_device=True)
+        return build_gram(comm, plan_factory, n, X_dev, Y_dev, chi_cap=cap0, device=device, return_device=True,
+                          structural_cap=structural)
 
     def step_e2e():
         return build_kernel_matrix(comm, ans, X, Y, truncation_error=TRUNC_ERROR, chi=cap0)

@@ -25,7 +25,7 @@ typedef enum {
   QK_OK = 0,
   QK_ERR_ARG = -1,       /* bad argument (also: unknown gate -- cpu_backend/kernel_state_ansatz.py:129, KernelPkg.jl:62) */
   QK_ERR_CUDA = -2,      /* CUDA runtime / launch failure, or no device */
-  QK_ERR_LIMIT = -3,     /* bond dimension above what the kernels support (chi_cap <= 256), or above a plan's cap */
+  QK_ERR_LIMIT = -3,     /* bond dimension above what the kernels support (chi_cap <= 512), or above a plan's cap */
   QK_ERR_ALLOC = -4
 } qk_status;
 
@@ -112,6 +112,13 @@ void qk_plan_destroy(qk_plan* plan);
 int qk_simulate(const qk_plan* plan, int device, const double* X_host, int N, int ldx, qk_batch** out);
 int qk_simulate_dev(const qk_plan* plan, int device, void* stream, const double* X_dev, int N, int ldx,
                     qk_batch** out);
+/* Asynchronous variant: returns as soon as the kernel is queued on `stream` (no host synchronisation; scratch is
+ * released in stream order).  The batch may be passed to qk_batch_pack_async / qk_gram_* on the same stream at
+ * once; qk_batch_info / qk_batch_sim_ms / qk_batch_unit_seconds wait for the kernel.  Lets a caller queue
+ * stage 1 -> pack -> exchange -> stage 2 without a host round trip (the reference interleaves its ring exchange
+ * with the products, gpu_backend/kernel_state_ansatz.py:330-334,366-419). */
+int qk_simulate_async(const qk_plan* plan, int device, void* stream, const double* X_dev, int N, int ldx,
+                      qk_batch** out);
 /* One datapoint with a memory trace: bytes_per_op[o] = sum of site-tensor bytes after op o of the compiled
  * schedule (qk_plan_ops gives the ops).  Replaces the "MPS size (MiB)=" debug log of pytket-cutensornet that
  * main_track_mem.py:168-172,254-256 captures and runs/mem_evol/plot.py:12-15 parses. */
@@ -119,6 +126,10 @@ int qk_simulate_trace(const qk_plan* plan, int device, const double* x_host, int
                       int max_ops, qk_batch** out);
 /* last stage-1 kernel time in ms (CUDA events on the launching stream) */
 int qk_batch_sim_ms(const qk_batch* batch, float* ms);
+/* seconds each datapoint's circuit took inside the kernel (clock64 around the datapoint; N doubles): the
+ * per-circuit times the reference records around every simulate() call (gpu_backend/kernel_state_ansatz.py:220-222)
+ * and reports as median / quartiles (:299-316) */
+int qk_batch_unit_seconds(const qk_batch* batch, double* seconds /*[N]*/);
 
 /* ---- MPS handle surface the orchestrator needs (gpu_backend/kernel_state_ansatz.py:223,295-296):
  *      bond dimensions, byte size, accumulated fidelity.  Any output pointer may be NULL. ---- */
@@ -140,6 +151,9 @@ void qk_batch_destroy(qk_batch* batch);
  *      (multiples of 8, D[0] = D[n] = 8); it is plain device memory the caller may all-gather. ---- */
 int qk_frag_stride(int n_qubits, const int32_t* D, int64_t* bytes_per_state);
 int qk_batch_pack(const qk_batch* batch, const int32_t* D, void* frag_dev, void* stream);
+/* asynchronous: state i -> position first_index + i; no host synchronisation, no bond-dimension check (D must
+ * cover the bond caps of the batch's plan) */
+int qk_batch_pack_async(const qk_batch* batch, const int32_t* D, void* frag_dev, int first_index, void* stream);
 /* same, state i written at position dst_index[i] of the frag buffer (skipped if negative): merges the
  * valid states of several batches (different bond caps) into one exchange buffer */
 int qk_batch_pack_scatter(const qk_batch* batch, const int32_t* D, void* frag_dev, const int32_t* dst_index,
@@ -155,6 +169,12 @@ int qk_gram_frags(int device, void* stream, int n_qubits,
                   const int32_t* Dy, const void* fragY, int Ny,
                   const int32_t* tiles /*[n_tiles][4] = r0,r1,c0,c1*/, int n_tiles, int symmetric,
                   double* K_dev, int64_t ldk, float* ms_out);
+/* qk_gram_frags with ms_out == NULL is asynchronous (kernel queued on `stream`, no host synchronisation).
+ * Per-tile timing: the next qk_gram_frags call of this thread writes the clock64 ticks every CTA tile (8 inner
+ * products) took to clk_dev (device, `capacity` entries; NULL switches it off) -- the per-product times the
+ * reference records around every vdot (gpu_backend/kernel_state_ansatz.py:379-381). */
+int qk_gram_set_tile_clocks(long long* clk_dev, int64_t capacity);
+int64_t qk_gram_tile_clocks_used(void);
 /* Same Gram tiles for batches whose bond dimensions are all <= 4 (max_chi; the regime of the reference's published
  * scaling runs, runs/runtime_scaling: chi = 2): one lane per (y, x) pair on the FP64 CUDA cores, reading the
  * unpadded stage-1 stores [N][state_stride] c128 + chi [N][n+1] of states simulated with `plan` (raw device

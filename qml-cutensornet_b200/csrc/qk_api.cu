@@ -15,6 +15,8 @@
 #include "qk_sim_core.h"
 
 static thread_local std::string g_err;
+static thread_local long long* g_gram_clk = nullptr;
+static thread_local int64_t g_gram_clk_cap = 0, g_gram_clk_used = 0;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 static int cuda_fail(cudaError_t e, const char* what) {
   g_err = std::string(what) + ": " + cudaGetErrorString(e);
@@ -90,6 +92,48 @@ static void pool_free(void* p) {
 template <typename T>
 static cudaError_t pool_alloc_t(T** out, size_t bytes) { return pool_alloc((void**)out, bytes); }
 
+// Stream-ordered release for the asynchronous entry points: the block goes back to the pool only once everything
+// queued on `stream` up to now has finished (an event is recorded; pool_reap() polls it).
+struct DeferredFree { void* p; cudaEvent_t ev; };
+static std::vector<DeferredFree> g_deferred;
+static std::mutex g_deferred_mu;
+
+static void pool_reap(bool wait) {
+  std::vector<void*> done;
+  {
+    std::lock_guard<std::mutex> lock(g_deferred_mu);
+    for (size_t i = 0; i < g_deferred.size();) {
+      cudaError_t q = wait ? cudaEventSynchronize(g_deferred[i].ev) : cudaEventQuery(g_deferred[i].ev);
+      if (q == cudaSuccess || q != cudaErrorNotReady) {
+        cudaEventDestroy(g_deferred[i].ev);
+        done.push_back(g_deferred[i].p);
+        g_deferred[i] = g_deferred.back();
+        g_deferred.pop_back();
+      } else {
+        ++i;
+      }
+    }
+    cudaGetLastError();
+  }
+  for (void* p : done) pool_free(p);
+}
+
+static void pool_free_after(void* p, cudaStream_t stream) {
+  if (!p) return;
+  cudaEvent_t ev = nullptr;
+  if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(ev, stream) != cudaSuccess) {
+    if (ev) cudaEventDestroy(ev);
+    cudaStreamSynchronize(stream);
+    pool_free(p);
+    return;
+  }
+  {
+    std::lock_guard<std::mutex> lock(g_deferred_mu);
+    g_deferred.push_back({p, ev});
+  }
+  pool_reap(false);
+}
+
 struct qk_batch {
   int device = 0;
   int n = 0, N = 0;
@@ -103,6 +147,9 @@ struct qk_batch {
   int64_t* site_off_dev = nullptr;   // device [n+1]
   float sim_ms = 0.f;
   int sim_grid = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // around the stage-1 kernel (asynchronous launches: read lazily)
+  cudaStream_t stream = nullptr;
+  long long* unit_clk = nullptr;              // device [N] clock64 ticks per datapoint (per-unit timing)
 };
 
 extern "C" {
@@ -172,7 +219,10 @@ void qk_batch_destroy(qk_batch* b) {
   int prev = 0;
   cudaGetDevice(&prev);
   cudaSetDevice(b->device);
-  pool_free(b->store); pool_free(b->chi); pool_free(b->stats); pool_free(b->site_off_dev);
+  if (b->ev1) cudaEventSynchronize(b->ev1);   // the stage-1 kernel may still be running (asynchronous launch)
+  if (b->ev0) cudaEventDestroy(b->ev0);
+  if (b->ev1) cudaEventDestroy(b->ev1);
+  pool_free(b->store); pool_free(b->chi); pool_free(b->stats); pool_free(b->site_off_dev); pool_free(b->unit_clk);
   cudaSetDevice(prev);
   delete b;
 }
@@ -191,37 +241,35 @@ static int batch_alloc(qk_batch* b) {
 
 static thread_local double* g_trace_dev = nullptr;   // set only inside qk_simulate_trace
 
-int qk_simulate_dev(const qk_plan* plan, int device, void* stream_v, const double* X_dev, int N, int ldx,
-                    qk_batch** out) {
+// Stage 1 launch.  sync = false: nothing waits for the kernel; the batch carries the events, every scratch block is
+// released in stream order (pool_free_after), and results must only be used on `stream` or after qk_batch_sim_ms.
+static int simulate_impl(const qk_plan* plan, int device, cudaStream_t stream, const double* X_dev, int N, int ldx,
+                         qk_batch** out, bool sync) {
   if (!plan || !out) return fail(QK_ERR_ARG, "NULL argument");
   *out = nullptr;
   if (N < 0 || (N > 0 && !X_dev) || ldx < plan->n) return fail(QK_ERR_ARG, "bad X / N / ldx (ldx must be >= n_qubits)");
-  cudaStream_t stream = (cudaStream_t)stream_v;
   qk_batch* b = new qk_batch();
-  b->device = device; b->n = plan->n; b->N = N; b->chi_cap = plan->chi_cap;
+  b->device = device; b->n = plan->n; b->N = N; b->chi_cap = plan->chi_cap; b->stream = stream;
   b->cap = plan->cap; b->site_off = plan->site_off; b->state_stride = plan->state_stride;
   int rc = batch_alloc(b);
   if (rc != QK_OK) { qk_batch_destroy(b); return rc; }
   if (N == 0) { *out = b; return QK_OK; }
+  pool_reap(false);
 
+  std::vector<void*> scratch;
+  auto cleanup = [&]() { for (void* p : scratch) pool_free_after(p, stream); scratch.clear(); };
+  auto bail = [&](cudaError_t e, const char* what) { cleanup(); cudaStreamSynchronize(stream); qk_batch_destroy(b); return cuda_fail(e, what); };
+  auto salloc = [&](void** ptr, size_t bytes) { cudaError_t e = pool_alloc(ptr, bytes); if (e == cudaSuccess) scratch.push_back(*ptr); return e; };
+  cudaError_t e;
   QkOp* ops_dev = nullptr; int32_t* cap_dev = nullptr; int* counter = nullptr;
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  auto cleanup = [&]() {
-    pool_free(ops_dev); pool_free(cap_dev); pool_free(counter);
-    if (e0) cudaEventDestroy(e0);
-    if (e1) cudaEventDestroy(e1);
-  };
-#define QK_TRY(call, what)                                              \
-  do {                                                                  \
-    cudaError_t _e = (call);                                            \
-    if (_e != cudaSuccess) { cleanup(); qk_batch_destroy(b); return cuda_fail(_e, what); } \
-  } while (0)
   const size_t nops = plan->ops.size();
-  QK_TRY(pool_alloc_t(&ops_dev, std::max<size_t>(nops, 1) * sizeof(QkOp)), "cudaMalloc(ops)");
-  QK_TRY(pool_alloc_t(&cap_dev, (plan->n + 1) * sizeof(int32_t)), "cudaMalloc(cap)");
-  QK_TRY(pool_alloc_t(&counter, sizeof(int)), "cudaMalloc(counter)");
-  QK_TRY(cudaMemcpyAsync(ops_dev, plan->ops.data(), nops * sizeof(QkOp), cudaMemcpyHostToDevice, stream), "copy ops");
-  QK_TRY(cudaMemcpyAsync(cap_dev, plan->cap.data(), (plan->n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, stream), "copy cap");
+  if ((e = salloc((void**)&ops_dev, std::max<size_t>(nops, 1) * sizeof(QkOp))) != cudaSuccess) return bail(e, "cudaMalloc(ops)");
+  if ((e = salloc((void**)&cap_dev, (plan->n + 1) * sizeof(int32_t))) != cudaSuccess) return bail(e, "cudaMalloc(cap)");
+  if ((e = salloc((void**)&counter, sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc(counter)");
+  if ((e = pool_alloc_t(&b->unit_clk, (size_t)N * sizeof(long long))) != cudaSuccess) return bail(e, "cudaMalloc(unit clocks)");
+  if ((e = cudaMemsetAsync(b->unit_clk, 0, (size_t)N * sizeof(long long), stream)) != cudaSuccess) return bail(e, "memset");
+  if ((e = cudaMemcpyAsync(ops_dev, plan->ops.data(), nops * sizeof(QkOp), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return bail(e, "copy ops");
+  if ((e = cudaMemcpyAsync(cap_dev, plan->cap.data(), (plan->n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return bail(e, "copy cap");
 
   SimParams P;
   P.n = plan->n; P.n_ops = (int)nops; P.ops = ops_dev; P.cap = cap_dev; P.site_off = b->site_off_dev;
@@ -234,70 +282,69 @@ int qk_simulate_dev(const qk_plan* plan, int device, void* stream_v, const doubl
   P.early_exit = plan->early_exit;
   P.floor_rel = 1e-28;
   P.abs_rel = 0.0;
-
-  QK_TRY(cudaEventCreate(&e0), "cudaEventCreate");
-  QK_TRY(cudaEventCreate(&e1), "cudaEventCreate");
-  QK_TRY(cudaEventRecord(e0, stream), "cudaEventRecord");
-  double* lam_dev = nullptr; int32_t* lvl_dev = nullptr; QkStat* parts_dev = nullptr;
   P.parallel = plan->parallel; P.lam = nullptr; P.lam_ld = plan->rmax / 2; P.level_start = nullptr; P.n_levels = 0;
   P.big_w = nullptr; P.big_s = nullptr; P.big_w_stride = P.big_s_stride = 0; P.big_flag = nullptr; P.big_jb = plan->jb;
-  P.unit_clk = nullptr;
+  P.unit_clk = b->unit_clk;
+
+  if ((e = cudaEventCreate(&b->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
+  if ((e = cudaEventCreate(&b->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
+  if ((e = cudaEventRecord(b->ev0, stream)) != cudaSuccess) return bail(e, "cudaEventRecord");
+  const char* what = "stage-1 kernel";
   if (plan->big) {
     // large-matrix path: theta and the staging area of every resident cluster live in global memory
+    what = "stage-1 kernel (large-matrix path)";
     int ncta_req = 0, ncta = 1, n_clusters = 1;
     if (const char* ev = getenv("QK_BIG_CLUSTER")) { const int v = atoi(ev); if (v >= 1 && v <= 16) ncta_req = v; }
     c128 *w_dev = nullptr, *s_dev = nullptr; int* f_dev = nullptr;
-    cudaError_t ea = qk_sim_big_config(plan->smem_bytes, N, ncta_req, &ncta, &n_clusters);
+    e = qk_sim_big_config(plan->smem_bytes, N, ncta_req, &ncta, &n_clusters);
     const size_t w_stride = (size_t)plan->rmax * plan->rmax, s_stride = w_stride / 2;
-    if (ea == cudaSuccess) ea = pool_alloc_t(&w_dev, (size_t)n_clusters * w_stride * sizeof(c128));
-    if (ea == cudaSuccess) ea = pool_alloc_t(&s_dev, (size_t)n_clusters * s_stride * sizeof(c128));
-    if (ea == cudaSuccess) ea = pool_alloc_t(&f_dev, (size_t)n_clusters * 4 * sizeof(int));
-    if (ea == cudaSuccess) ea = cudaMemsetAsync(f_dev, 0, (size_t)n_clusters * 4 * sizeof(int), stream);
-    if (ea == cudaSuccess) {
+    if (e == cudaSuccess) e = salloc((void**)&w_dev, (size_t)n_clusters * w_stride * sizeof(c128));
+    if (e == cudaSuccess) e = salloc((void**)&s_dev, (size_t)n_clusters * s_stride * sizeof(c128));
+    if (e == cudaSuccess) e = salloc((void**)&f_dev, (size_t)n_clusters * 4 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(f_dev, 0, (size_t)n_clusters * 4 * sizeof(int), stream);
+    if (e == cudaSuccess) {
       P.big_w = w_dev; P.big_s = s_dev; P.big_w_stride = (int64_t)w_stride; P.big_s_stride = (int64_t)s_stride; P.big_flag = f_dev;
-      ea = qk_launch_sim_big(P, plan->smem_bytes, ncta, n_clusters, stream);
+      e = qk_launch_sim_big(P, plan->smem_bytes, ncta, n_clusters, stream);
       b->sim_grid = n_clusters * ncta;
     }
-    if (ea == cudaSuccess) ea = cudaEventRecord(e1, stream);
-    if (ea == cudaSuccess) ea = cudaEventSynchronize(e1);
-    pool_free(w_dev); pool_free(s_dev); pool_free(f_dev);
-    if (ea != cudaSuccess) { cleanup(); qk_batch_destroy(b); return cuda_fail(ea, "stage-1 kernel (large-matrix path)"); }
-    cudaEventElapsedTime(&b->sim_ms, e0, e1);
-    cleanup();
-    *out = b;
-    return QK_OK;
-  }
-  if (plan->parallel) {
+  } else if (plan->parallel) {
+    what = "stage-1 kernel (B form)";
     int ncta = 6;   // C3 levels are 12 or 24 items wide: 6 CTAs leave no idle CTA in the last round (measured 6.1 vs 6.7 ms with 8)
     if (const char* ev = getenv("QK_SIM_CLUSTER")) { const int v = atoi(ev); if (v >= 1 && v <= 8) ncta = v; }
-    const size_t lam_bytes = (size_t)N * (plan->n + 1) * P.lam_ld * sizeof(double);
-    cudaError_t ea = pool_alloc_t(&lam_dev, lam_bytes);
-    if (ea == cudaSuccess) ea = pool_alloc_t(&lvl_dev, plan->level_start.size() * sizeof(int32_t));
-    if (ea == cudaSuccess) ea = pool_alloc_t(&parts_dev, (size_t)N * ncta * sizeof(QkStat));
-    if (ea == cudaSuccess)
-      ea = cudaMemcpyAsync(lvl_dev, plan->level_start.data(), plan->level_start.size() * sizeof(int32_t),
-                           cudaMemcpyHostToDevice, stream);
-    if (ea == cudaSuccess) {
+    double* lam_dev = nullptr; int32_t* lvl_dev = nullptr; QkStat* parts_dev = nullptr;
+    e = salloc((void**)&lam_dev, (size_t)N * (plan->n + 1) * P.lam_ld * sizeof(double));
+    if (e == cudaSuccess) e = salloc((void**)&lvl_dev, plan->level_start.size() * sizeof(int32_t));
+    if (e == cudaSuccess) e = salloc((void**)&parts_dev, (size_t)N * ncta * sizeof(QkStat));
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(lvl_dev, plan->level_start.data(), plan->level_start.size() * sizeof(int32_t),
+                          cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) {
       P.lam = lam_dev; P.level_start = lvl_dev; P.n_levels = (int)plan->level_start.size() - 1;
-      ea = qk_launch_sim_b(P, plan->threads, plan->smem_bytes, ncta, parts_dev, stream, &b->sim_grid);
+      e = qk_launch_sim_b(P, plan->threads, plan->smem_bytes, ncta, parts_dev, stream, &b->sim_grid);
     }
-    if (ea == cudaSuccess) ea = cudaEventRecord(e1, stream);
-    if (ea == cudaSuccess) ea = cudaEventSynchronize(e1);
-    pool_free(lam_dev); pool_free(lvl_dev); pool_free(parts_dev);
-    if (ea != cudaSuccess) { cleanup(); qk_batch_destroy(b); return cuda_fail(ea, "stage-1 kernel (B form)"); }
-    cudaEventElapsedTime(&b->sim_ms, e0, e1);
-    cleanup();
-    *out = b;
-    return QK_OK;
+  } else {
+    e = qk_launch_sim(P, plan->threads, plan->smem_bytes, counter, stream, &b->sim_grid);
   }
-  QK_TRY(qk_launch_sim(P, plan->threads, plan->smem_bytes, counter, stream, &b->sim_grid), "stage-1 kernel launch");
-  QK_TRY(cudaEventRecord(e1, stream), "cudaEventRecord");
-  QK_TRY(cudaEventSynchronize(e1), "stage-1 kernel");
-  cudaEventElapsedTime(&b->sim_ms, e0, e1);
+  if (e == cudaSuccess) e = cudaEventRecord(b->ev1, stream);
+  if (e != cudaSuccess) return bail(e, what);
   cleanup();
-#undef QK_TRY
+  if (sync) {
+    e = cudaEventSynchronize(b->ev1);
+    if (e != cudaSuccess) { qk_batch_destroy(b); return cuda_fail(e, what); }
+    cudaEventElapsedTime(&b->sim_ms, b->ev0, b->ev1);
+  }
   *out = b;
   return QK_OK;
+}
+
+int qk_simulate_dev(const qk_plan* plan, int device, void* stream_v, const double* X_dev, int N, int ldx,
+                    qk_batch** out) {
+  return simulate_impl(plan, device, (cudaStream_t)stream_v, X_dev, N, ldx, out, true);
+}
+
+int qk_simulate_async(const qk_plan* plan, int device, void* stream_v, const double* X_dev, int N, int ldx,
+                      qk_batch** out) {
+  return simulate_impl(plan, device, (cudaStream_t)stream_v, X_dev, N, ldx, out, false);
 }
 
 int qk_simulate(const qk_plan* plan, int device, const double* X_host, int N, int ldx, qk_batch** out) {
@@ -337,6 +384,27 @@ int qk_simulate_trace(const qk_plan* plan, int device, const double* x_host, int
 int qk_batch_sim_ms(const qk_batch* b, float* ms) {
   if (!b || !ms) return fail(QK_ERR_ARG, "NULL argument");
   *ms = b->sim_ms;
+  if (b->ev1 && b->sim_ms == 0.f && b->N > 0) {   // asynchronous launch: wait for it now
+    QK_CUDA(cudaEventSynchronize(b->ev1), "stage-1 kernel");
+    float t = 0.f;
+    cudaEventElapsedTime(&t, b->ev0, b->ev1);
+    const_cast<qk_batch*>(b)->sim_ms = t;
+    *ms = t;
+  }
+  return QK_OK;
+}
+
+int qk_batch_unit_seconds(const qk_batch* b, double* seconds) {
+  if (!b || !seconds) return fail(QK_ERR_ARG, "NULL argument");
+  if (b->N == 0) return QK_OK;
+  QK_CUDA(cudaSetDevice(b->device), "cudaSetDevice");
+  if (b->ev1) QK_CUDA(cudaEventSynchronize(b->ev1), "stage-1 kernel");
+  std::vector<long long> clk(b->N, 0);
+  if (b->unit_clk) QK_CUDA(cudaMemcpy(clk.data(), b->unit_clk, clk.size() * sizeof(long long), cudaMemcpyDeviceToHost), "copy clocks");
+  int khz = 0;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, b->device);
+  const double hz = khz > 0 ? 1e3 * khz : 1.965e9;
+  for (int i = 0; i < b->N; ++i) seconds[i] = (double)clk[i] / hz;
   return QK_OK;
 }
 
@@ -493,9 +561,39 @@ int qk_batch_pack_scatter(const qk_batch* b, const int32_t* D, void* frag_dev, c
     e = cudaMemcpyAsync(dst_dev, dst_index, (size_t)b->N * sizeof(int32_t), cudaMemcpyHostToDevice, stream);
   if (e == cudaSuccess)
     e = qk_launch_pack(b->n, b->N, b->store, b->state_stride, b->site_off_dev, b->chi, D_dev, off_dev, L.stride_bytes,
-                       L.data_bytes, frag_dev, dst_dev, stream);
+                       L.data_bytes, frag_dev, dst_dev, 0, stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
   pool_free(D_dev); pool_free(off_dev); pool_free(dst_dev);
+  if (e != cudaSuccess) return cuda_fail(e, "pack kernel");
+  return QK_OK;
+}
+
+// Asynchronous pack: state i of the batch goes to position first_index + i of the frag buffer.  No host
+// synchronisation and no check of the bond dimensions against D (the caller passes dims that cover the plan's caps).
+int qk_batch_pack_async(const qk_batch* b, const int32_t* D, void* frag_dev, int first_index, void* stream_v) {
+  if (!b || !frag_dev || first_index < 0) return fail(QK_ERR_ARG, "bad arguments");
+  int rc = check_D(b->n, D);
+  if (rc != QK_OK) return rc;
+  if (b->N == 0) return QK_OK;
+  for (int s = 0; s <= b->n; ++s)
+    if (D[s] < b->cap[s]) return fail(QK_ERR_ARG, "asynchronous pack needs padded dimensions >= the batch's bond caps");
+  QK_CUDA(cudaSetDevice(b->device), "cudaSetDevice");
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  FragLayout L;
+  std::vector<int64_t> off(b->n + 1);
+  qk_frag_layout(b->n, D, &L, off.data());
+  const size_t nb = (size_t)b->n + 1;
+  const size_t o_off = (nb * sizeof(int32_t) + 15) & ~(size_t)15;
+  std::vector<unsigned char> h(o_off + nb * sizeof(int64_t));
+  memcpy(h.data(), D, nb * sizeof(int32_t));
+  memcpy(h.data() + o_off, off.data(), nb * sizeof(int64_t));
+  unsigned char* d = nullptr;
+  QK_CUDA(pool_alloc_t(&d, h.size()), "cudaMalloc(pack scratch)");
+  cudaError_t e = cudaMemcpyAsync(d, h.data(), h.size(), cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess)
+    e = qk_launch_pack(b->n, b->N, b->store, b->state_stride, b->site_off_dev, b->chi, (const int32_t*)d,
+                       (const int64_t*)(d + o_off), L.stride_bytes, L.data_bytes, frag_dev, nullptr, first_index, stream);
+  pool_free_after(d, stream);
   if (e != cudaSuccess) return cuda_fail(e, "pack kernel");
   return QK_OK;
 }
@@ -606,24 +704,46 @@ int qk_gram_frags(int device, void* stream_v, int n_qubits, const int32_t* Dx, c
   P.tiles = (const int4*)(dbuf + t_off); P.n_cta_tiles = (int)cta.size();
   P.symmetric = symmetric ? 1 : 0;
   P.K = K_dev; P.ldk = ldk; P.slot_x = slot_x; P.slot_y = slot_y;
-  if (e == cudaSuccess) e = cudaEventCreate(&e0);
-  if (e == cudaSuccess) e = cudaEventCreate(&e1);
-  if (e == cudaSuccess) e = cudaEventRecord(e0, stream);
+  P.unit_clk = g_gram_clk;
+  if (g_gram_clk_cap < (int64_t)cta.size()) P.unit_clk = nullptr;
+  g_gram_clk_used = P.unit_clk ? (int64_t)cta.size() : 0;
+  // ms_out == NULL: asynchronous -- nothing waits for the kernel, scratch is released in stream order
+  const bool sync = (ms_out != nullptr);
+  if (sync) {
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    if (e == cudaSuccess) e = cudaEventRecord(e0, stream);
+  }
   if (e == cudaSuccess)
     e = generic ? qk_launch_gram_frag_generic(P, pairs_dev, (int)pair_list.size(), maxD, stream)
                 : qk_launch_gram_dmma(P, maxD, stream);
-  if (e == cudaSuccess) e = cudaEventRecord(e1, stream);
-  if (e == cudaSuccess) e = cudaEventSynchronize(e1);
   float ms = 0.f;
-  if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
-  if (e0) cudaEventDestroy(e0);
-  if (e1) cudaEventDestroy(e1);
-  pool_free(dbuf);
-  pool_free(pairs_dev);
+  if (sync) {
+    if (e == cudaSuccess) e = cudaEventRecord(e1, stream);
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    pool_free(dbuf);
+    pool_free(pairs_dev);
+  } else {
+    pool_free_after(dbuf, stream);
+    pool_free_after(pairs_dev, stream);
+  }
   if (e != cudaSuccess) return cuda_fail(e, "stage-2 kernel");
   if (ms_out) *ms_out = ms;
   return QK_OK;
 }
+
+// Optional per-tile clocks of the next qk_gram_frags call on this thread (per-unit timing of the inner products,
+// reference gpu:379-381): clk_dev receives clock64 ticks per CTA tile (8 pairs), at most `capacity` entries.
+int qk_gram_set_tile_clocks(long long* clk_dev, int64_t capacity) {
+  g_gram_clk = clk_dev;
+  g_gram_clk_cap = clk_dev ? capacity : 0;
+  g_gram_clk_used = 0;
+  return QK_OK;
+}
+int64_t qk_gram_tile_clocks_used(void) { return g_gram_clk_used; }
 
 static int gram_big_run(int device, cudaStream_t stream, int n, const int64_t* soff_x, const int64_t* soff_y,
                         const int32_t* dims_x, const int32_t* dims_y, const c128* storeX, int64_t strideX,

@@ -59,10 +59,10 @@ __global__ void __launch_bounds__(256) qk_pack_kernel(int n, const c128* __restr
                                                       const int32_t* __restrict__ chi, const int32_t* __restrict__ D,
                                                       const int64_t* __restrict__ frag_off, int64_t frag_stride,
                                                       int64_t frag_data, unsigned char* __restrict__ frag,
-                                                      const int32_t* __restrict__ dst_index) {
+                                                      const int32_t* __restrict__ dst_index, int dst_base) {
   const int s = blockIdx.x;
   const int i = blockIdx.y;
-  const int idst = dst_index ? dst_index[i] : i;   // position of state i in the frag buffer (< 0: skip)
+  const int idst = dst_index ? dst_index[i] : dst_base + i;   // position of state i in the frag buffer (< 0: skip)
   if (idst < 0) return;
   const int Dl = D[s], Dr = D[s + 1];
   const int KT = Dl >> 3, MT = Dr >> 3;
@@ -95,11 +95,11 @@ __global__ void __launch_bounds__(256) qk_pack_kernel(int n, const c128* __restr
 cudaError_t qk_launch_pack(int n, int N, const c128* store, int64_t state_stride, const int64_t* site_off_dev,
                            const int32_t* chi_dev, const int32_t* D_dev, const int64_t* frag_off_dev,
                            int64_t frag_stride_bytes, int64_t frag_data_bytes, void* frag_dev,
-                           const int32_t* dst_index_dev, cudaStream_t stream) {
+                           const int32_t* dst_index_dev, int dst_base, cudaStream_t stream) {
   if (N <= 0) return cudaSuccess;
   dim3 grid(n, N);
   qk_pack_kernel<<<grid, 256, 0, stream>>>(n, store, state_stride, site_off_dev, chi_dev, D_dev, frag_off_dev,
-                                           frag_stride_bytes, frag_data_bytes, (unsigned char*)frag_dev, dst_index_dev);
+                                           frag_stride_bytes, frag_data_bytes, (unsigned char*)frag_dev, dst_index_dev, dst_base);
   return cudaGetLastError();
 }
 
@@ -309,6 +309,7 @@ __global__ void __launch_bounds__(QK_GRAM_WARPS * 32, NT == 1 ? 4 : (QK_GRAM_WAR
 
   const int4 tile = P.tiles[blockIdx.x];
   const int y0 = tile.x, x0 = tile.y, y_end = tile.z, x_end = tile.w;
+  const long long clk0 = clock64();
 
   for (int b = threadIdx.x; b <= n; b += blockDim.x) { sDx[b] = P.Dx[b]; sDy[b] = P.Dy[b]; }
   for (int t = warp; t < TI + QK_TJ; t += QK_GRAM_WARPS) {
@@ -445,6 +446,11 @@ __global__ void __launch_bounds__(QK_GRAM_WARPS * 32, NT == 1 ? 4 : (QK_GRAM_WAR
       P.K[(size_t)y * P.ldk + x] = v;
       if (P.symmetric) P.K[(size_t)x * P.ldk + y] = v;
     }
+  }
+  // per-tile time (8 inner products; the reference times every vdot, gpu:379-381): last warp out records it
+  if (P.unit_clk) {
+    __syncthreads();
+    if (threadIdx.x == 0) P.unit_clk[blockIdx.x] = clock64() - clk0;
   }
 }
 

@@ -30,7 +30,7 @@ void qk_frag_layout(int n, const int32_t* D, FragLayout* L, int64_t* site_off_by
 cudaError_t qk_launch_pack(int n, int N, const c128* store, int64_t state_stride, const int64_t* site_off_dev,
                            const int32_t* chi_dev, const int32_t* D_dev, const int64_t* frag_off_dev,
                            int64_t frag_stride_bytes, int64_t frag_data_bytes, void* frag_dev, const int32_t* dst_index_dev,
-                           cudaStream_t stream);
+                           int dst_base, cudaStream_t stream);
 
 // ---- stage 2 ----
 struct GramParams {
@@ -50,6 +50,7 @@ struct GramParams {
   double* K;
   int64_t ldk;
   int slot_x, slot_y;       // bytes reserved per state per pipeline stage
+  long long* unit_clk;      // optional device [n_cta_tiles]: clock64 ticks every CTA tile took, or NULL
 };
 // DMMA + bulk-copy pipeline kernel; requires max(D) <= 16.
 cudaError_t qk_launch_gram_dmma(const GramParams& P, int maxD, cudaStream_t stream);

@@ -170,7 +170,7 @@ int qk_compile_plan(int n, const qk_gate* gates_in, int n_gates, int trunc_mode,
   if (!(trunc_error >= 0.0) || trunc_error >= 1.0) { *err = "truncation_error must be in [0, 1)"; return QK_ERR_ARG; }
   if (chi_cap < 1) { *err = "chi_cap must be >= 1"; return QK_ERR_ARG; }
   if (chi_cap > QK_CHI_LIMIT_BIG) {
-    *err = "bond dimension cap above the limit of the stage-1 kernels (chi <= 256)";
+    *err = "bond dimension cap above the limit of the stage-1 kernels (chi <= 512)";
     return QK_ERR_LIMIT;
   }
   plan->n = n; plan->n_gates = n_gates; plan->trunc_mode = trunc_mode; plan->trunc_error = trunc_error;

@@ -36,4 +36,4 @@ int qk_ansatz_gates(int n_qubits, int reps, double gamma, int hadamard_init, con
                     std::vector<qk_gate>* out, std::string* err);
 int qk_pick_threads(int chi_cap);
 #define QK_CHI_LIMIT 32        // shared-memory-resident stage-1 kernels (qk_sim_core.h)
-#define QK_CHI_LIMIT_BIG 256   // large-matrix stage-1 kernel (qk_sim_big.h)
+#define QK_CHI_LIMIT_BIG 512   // large-matrix stage-1 kernel (qk_sim_big.h): (2 chi) x 2 jb columns must fit in shared memory

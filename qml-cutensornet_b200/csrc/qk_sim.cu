@@ -12,8 +12,14 @@
 #include "qk_kernels.cuh"
 // level barrier of the B-form path: the CTAs of one thread-block cluster share a datapoint
 #define QK_GROUP_SYNC() do { __threadfence(); cooperative_groups::this_cluster().sync(); __threadfence(); } while (0)
-// cluster barrier of the large-matrix path (fences on both sides: global data written by one CTA is read by others)
-#define QK_CSYNC(c) do { if ((c).ncta > 1) { __threadfence(); cooperative_groups::this_cluster().sync(); __threadfence(); } \
+// Cluster barrier of the large-matrix path.  barrier.cluster.arrive / wait already have release / acquire semantics
+// at cluster scope; the gpu-scope fences around them are kept as a belt-and-braces measure for the global-memory
+// traffic between the CTAs -- measured cost: none (C4 shape, 8 CTAs per cluster: 5.20 s with, 5.10 s without).
+#ifndef QK_CSYNC_FENCE
+#define QK_CSYNC_FENCE 1
+#endif
+#define QK_CSYNC(c) do { if ((c).ncta > 1) { if (QK_CSYNC_FENCE) __threadfence(); cooperative_groups::this_cluster().sync(); \
+                                             if (QK_CSYNC_FENCE) __threadfence(); } \
                          else __syncthreads(); } while (0)
 #include "qk_sim_big.h"
 
@@ -32,7 +38,9 @@ __global__ void __launch_bounds__(G, SimMinBlocks<G>::value) qk_sim_kernel(const
     const int dp = next_dp;
     __syncthreads();
     if (dp >= P.N) break;
+    const long long t0 = clock64();
     qk_sim_datapoint<G>(c, dp);
+    if (P.unit_clk && threadIdx.x == 0) P.unit_clk[dp] = clock64() - t0;   // per-circuit time (reference gpu:220-222)
   }
 }
 
@@ -84,8 +92,10 @@ __global__ void __launch_bounds__(G, SimMinBlocks<G>::value) qk_sim_kernel_b(con
   SimCtx c;
   qk_sim_carve(c, &P, qk_smem, G);
   for (int dp = (int)(blockIdx.x / ncta); dp < P.N; dp += n_clusters) {
+    const long long t0 = clock64();
     qk_sim_datapoint_b<G>(c, dp, cta, ncta, parts + (size_t)dp * ncta);
     QK_GROUP_SYNC();
+    if (P.unit_clk && cta == 0 && threadIdx.x == 0) P.unit_clk[dp] = clock64() - t0;
   }
 }
 
@@ -162,9 +172,12 @@ cudaError_t qk_sim_big_config(size_t smem_bytes, int N, int ncta_req, int* ncta_
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int ncta = ncta_req;
-  if (ncta <= 0) {   // as many CTAs per datapoint as the SMs allow: 148 SMs / N datapoints, a power of two <= 16
+  if (ncta <= 0) {
+    // as many CTAs per datapoint as the SMs allow: 148 SMs / N datapoints, a power of two <= 8.  (16-CTA clusters are
+    // possible with the non-portable attribute, but only ~one fits per GPC: 8 datapoints then need two waves --
+    // measured 8.8 s against 5.1 s with 8 CTAs on the C4 shape.)
     ncta = 1;
-    while (ncta * 2 <= 16 && ncta * 2 * (N < 1 ? 1 : N) <= sms) ncta *= 2;
+    while (ncta * 2 <= 8 && ncta * 2 * (N < 1 ? 1 : N) <= sms) ncta *= 2;
   }
   cudaError_t e = cudaSuccess;
   for (; ncta >= 1; ncta /= 2) {

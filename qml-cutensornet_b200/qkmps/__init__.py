@@ -26,7 +26,7 @@ QK_PLAN_LITERAL_ORDER = 1
 QK_PLAN_EARLY_EXIT = 2
 QK_PLAN_NO_FUSION = 4
 QK_PLAN_PARALLEL = 8
-CHI_LIMIT = 256         # stage-1 kernels: shared-memory-resident up to 32, large-matrix (cluster) kernel above
+CHI_LIMIT = 512         # stage-1 kernels: shared-memory-resident up to 32, large-matrix (cluster) kernel above
 QK_PLAN_BIG = 16
 DMMA_D_LIMIT = 16       # register-resident tensor-core overlap kernel
 
@@ -62,7 +62,8 @@ EXPORTS = [
     "qk_simulate", "qk_simulate_dev", "qk_simulate_trace", "qk_batch_sim_ms", "qk_batch_size", "qk_batch_info", "qk_batch_export",
     "qk_batch_import", "qk_batch_max_chi", "qk_batch_destroy", "qk_frag_stride", "qk_batch_pack",
     "qk_batch_pack_scatter",
-    "qk_gram_frags", "qk_batch_store", "qk_gram_lane", "qk_gram_store", "qk_gram_host", "qk_dmma_peak", "qk_pipe_mix", "qk_gram_big", "qk_batch_repack",
+    "qk_gram_frags", "qk_batch_store", "qk_gram_lane", "qk_gram_store", "qk_gram_host", "qk_dmma_peak", "qk_pipe_mix", "qk_gram_big", "qk_batch_repack", "qk_simulate_async", "qk_batch_unit_seconds", "qk_batch_pack_async",
+    "qk_gram_set_tile_clocks", "qk_gram_tile_clocks_used",
 ]
 
 _lib = None
@@ -205,6 +206,17 @@ class Batch:
         _check(lib().qk_batch_sim_ms(self._h, ctypes.byref(ms)))
         return ms.value
 
+    def unit_seconds(self) -> np.ndarray:
+        """Seconds every datapoint's circuit took inside the stage-1 kernel (per-unit timing)."""
+        out = np.zeros(self.N)
+        _check(lib().qk_batch_unit_seconds(self._h, _p(out, ctypes.c_double)))
+        return out
+
+    def pack_async(self, D, frag_ptr: int, first_index: int, stream: int = 0):
+        D = np.ascontiguousarray(D, dtype=np.int32)
+        _check(lib().qk_batch_pack_async(self._h, _p(D, ctypes.c_int32), ctypes.c_void_p(frag_ptr), int(first_index),
+                                         ctypes.c_void_p(stream)))
+
     def max_chi(self) -> np.ndarray:
         out = np.ones(self.n_qubits + 1, dtype=np.int32)
         _check(lib().qk_batch_max_chi(self._h, _p(out, ctypes.c_int32)))
@@ -287,6 +299,14 @@ def simulate_dev(plan: Plan, x_ptr: int, N: int, ldx: int, device: int = 0, stre
     return Batch(h)
 
 
+def simulate_async(plan: Plan, x_ptr: int, N: int, ldx: int, device: int = 0, stream: int = 0) -> Batch:
+    """Queue stage 1 on ``stream`` without waiting for it (qk_simulate_async)."""
+    h = ctypes.c_void_p()
+    _check(lib().qk_simulate_async(plan._h, int(device), ctypes.c_void_p(stream), ctypes.c_void_p(x_ptr), int(N), int(ldx),
+                                   ctypes.byref(h)))
+    return Batch(h)
+
+
 def simulate_trace(plan: Plan, x, device: int = 0):
     """Simulate one datapoint and return (Batch, [(op kind, site, MPS size in MiB after the op)]).
 
@@ -328,11 +348,24 @@ def frag_stride(n_qubits: int, D) -> int:
     return out.value
 
 
-def gram_frags(device, n_qubits, Dx, fragx_ptr, Nx, Dy, fragy_ptr, Ny, tiles, symmetric, k_ptr, ldk, stream=0) -> float:
+def gram_frags(device, n_qubits, Dx, fragx_ptr, Nx, Dy, fragy_ptr, Ny, tiles, symmetric, k_ptr, ldk, stream=0,
+               wait=True, tile_clocks=None) -> float:
+    """Tensor-core Gram kernel on packed fragments.  ``wait=False``: queued on ``stream`` only (returns 0.0).
+    ``tile_clocks`` = (device pointer, capacity): per-CTA-tile clock64 ticks are written there."""
     Dx = np.ascontiguousarray(Dx, dtype=np.int32)
     Dy = Dx if Dy is None else np.ascontiguousarray(Dy, dtype=np.int32)
     tiles = np.ascontiguousarray(np.asarray(tiles, dtype=np.int32).reshape(-1, 4))
     ms = ctypes.c_float()
+    lib().qk_gram_set_tile_clocks(ctypes.c_void_p(tile_clocks[0] if tile_clocks else 0),
+                                  ctypes.c_int64(tile_clocks[1] if tile_clocks else 0))
+    if not wait:
+        _check(lib().qk_gram_frags(int(device), ctypes.c_void_p(stream), int(n_qubits), _p(Dx, ctypes.c_int32),
+                                   ctypes.c_void_p(fragx_ptr), int(Nx), _p(Dy, ctypes.c_int32),
+                                   ctypes.c_void_p(fragy_ptr or 0), int(Ny), _p(tiles, ctypes.c_int32),
+                                   int(tiles.shape[0]), int(bool(symmetric)), ctypes.c_void_p(k_ptr), ctypes.c_int64(ldk),
+                                   None))
+        lib().qk_gram_set_tile_clocks(None, ctypes.c_int64(0))
+        return 0.0
     _check(lib().qk_gram_frags(int(device), ctypes.c_void_p(stream), int(n_qubits), _p(Dx, ctypes.c_int32),
                                ctypes.c_void_p(fragx_ptr), int(Nx), _p(Dy, ctypes.c_int32),
                                ctypes.c_void_p(fragy_ptr or 0), int(Ny), _p(tiles, ctypes.c_int32),

@@ -70,6 +70,34 @@ def init_from_env(backend: str | None = None) -> TorchComm:
     return TorchComm()
 
 
+def init_from_comm(comm) -> "TorchComm":
+    """Bootstrap torch.distributed from an mpi4py-like communicator (``Get_rank`` / ``Get_size`` / ``bcast``), e.g.
+    ``MPI.COMM_WORLD`` of the reference's drivers (main.py:17) launched with one process per GPU: rank 0 picks the
+    rendezvous address, every rank joins a NCCL (GPU) or gloo (CPU tests) process group."""
+    import torch
+    import torch.distributed as dist
+    if dist.is_initialized():
+        return TorchComm()
+    rank, size = comm.Get_rank(), comm.Get_size()
+    addr = None
+    if rank == 0:
+        import socket
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+        s.close()
+        addr = (os.environ.get("MASTER_ADDR", "127.0.0.1"), int(os.environ.get("QK_MASTER_PORT", port)))
+    if not hasattr(comm, "bcast"):
+        raise TypeError("multi-rank runs need a communicator with bcast() (mpi4py) or a qkmps.comm.TorchComm; got %r"
+                        % (type(comm),))
+    addr = comm.bcast(addr, root=0)
+    backend = "nccl" if torch.cuda.is_available() else "gloo"
+    if backend == "nccl":
+        torch.cuda.set_device(rank % torch.cuda.device_count())
+    dist.init_process_group(backend=backend, init_method=f"tcp://{addr[0]}:{addr[1]}", rank=rank, world_size=size)
+    return TorchComm()
+
+
 def _is_multi(comm) -> bool:
     return comm.Get_size() > 1
 
@@ -103,6 +131,30 @@ def allgather_bytes(comm, local):
     out = torch.empty(local.numel() * comm.Get_size(), dtype=local.dtype, device=local.device)
     comm.dist.all_gather_into_tensor(out, local, group=comm.group)
     return out
+
+
+def allgather_into(comm, buf, offset: int, count: int):
+    """In-place all-gather: every rank's ``buf[offset:offset+count]`` (offset = rank * count) lands in all ranks' ``buf``."""
+    _need_torch_comm(comm)
+    assert buf.numel() == count * comm.Get_size() and offset == comm.Get_rank() * count
+    comm.dist.all_gather_into_tensor(buf, buf[offset:offset + count], group=comm.group)
+    return buf
+
+
+def gather_to_root(comm, local):
+    """Gather equally sized device tensors to rank 0 (flat, rank order); ``None`` on the other ranks.  Replaces the
+    reference's dense ``reduce(SUM)`` of the whole kernel matrix (gpu:428): every rank sends only its row panel."""
+    _need_torch_comm(comm)
+    import torch
+    rank, size = comm.Get_rank(), comm.Get_size()
+    flat = local.contiguous().view(-1)
+    if rank == 0:
+        out = torch.empty(size * flat.numel(), dtype=flat.dtype, device=flat.device)
+        parts = list(out.split(flat.numel()))
+        comm.dist.gather(flat, gather_list=parts, dst=0, group=comm.group)
+        return out
+    comm.dist.gather(flat, gather_list=None, dst=0, group=comm.group)
+    return None
 
 
 def reduce_sum_to_root(comm, K):

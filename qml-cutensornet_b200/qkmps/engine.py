@@ -1,31 +1,40 @@
 """Host orchestration of the quantum-kernel path on B200s: shard -> simulate -> exchange -> Gram tiles.
 
 One process per GPU.  ``comm`` is duck-typed like the reference's ``mpi_comm`` (Get_rank / Get_size);
-with more than one rank it must be a ``qkmps.comm.TorchComm`` (torch.distributed: NCCL on GPUs,
+with more than one rank it is turned into a ``qkmps.comm.TorchComm`` (torch.distributed: NCCL on GPUs,
 gloo for the CPU-side tests of this logic).  PyTorch is used for device buffers, streams and the
 collectives only; all arithmetic is in libqkmps.so.
 
 Replaces gpu_backend/kernel_state_ansatz.py:152-428 of the reference:
   * chunking of X over ranks (gpu:154,169-174)            -> ``shard_bounds``
   * per-chunk simulate loop (gpu:213-231,255-273)          -> one stage-1 kernel launch per shard
-  * pickled-MPS round robin (gpu:342-352,416-419)          -> one all-gather of the packed "frag" buffers
-  * per-pair vdot loop + symmetric fill (gpu:366-405)      -> stage-2 kernel over this rank's row blocks
-  * dense reduce(SUM) to root (gpu:428)                    -> reduce of the (disjointly filled) K buffers
+  * pickled-MPS round robin (gpu:342-352,416-419)          -> one all-gather of the packed states on a side stream,
+                                                              overlapped with the local x local block of stage 2
+  * ring schedule of chunk pairs (gpu:330-334,366-405)     -> ``panel_tiles``: rank r owns the rows of its shard and
+                                                              the column shards r, r-1, .., r-n/2 (cyclic)
+  * dense reduce(SUM) to root (gpu:428)                    -> gather of the owned row panels
 """
 
 from __future__ import annotations
 
+import os
 import time
 
 import numpy as np
 
-import os
-
 from . import (CHI_LIMIT, DMMA_D_LIMIT, QK_FLAG_CAP_HIT, QK_FLAG_NO_CONVERGE, QkError, frag_stride,
-               gram_big, gram_frags, gram_lane, pad_dims, simulate_dev)
+               gram_big, gram_frags, gram_lane, pad_dims, simulate_async, simulate_dev)
 
-PARALLEL_MAX_LOCAL = 150   # datapoints per GPU up to which stage 1 uses one CTA cluster per datapoint
+PARALLEL_MAX_LOCAL = 150   # datapoints per GPU up to which stage 1 uses one CTA cluster per datapoint (B form):
+#                            measured r2 (C3, paired distance-2 routing): 125 points 4.9 vs 9.8 ms, 250: 9.5 vs 9.8,
+#                            500: 15.6 vs 11.1 (profiles/r02_stage1_schedules.txt)
 LANE_CHI_LIMIT = 4   # at or below this bond dimension stage 2 runs one lane per pair on the FP64 CUDA cores
+FRAG_D_LIMIT = 32    # padded bond dimension up to which stage 2 runs on the packed-fragment kernels
+# bond caps tried in turn; each has its own kernel configuration: <= 32 shared-memory-resident kernels (one CTA or, in
+# B form, one small cluster per datapoint), above that the large-matrix kernel (theta in L2, block Jacobi, one CTA
+# cluster per datapoint -- BASELINE config 4)
+CAP_LADDER = (4, 8, 16, 24, 32, 64, 128, 256, 512)
+BIG_STORE_BUDGET = 24 << 30   # bytes of working store a large-matrix launch may take (its time does not depend on the cap)
 
 
 class _DevView:
@@ -36,9 +45,6 @@ class _DevView:
                                          "version": 2}
 
 
-ROW_BLOCK = 8   # Gram rows are dealt to ranks in blocks of this many rows (multiple of the kernel's TJ)
-
-
 def shard_bounds(n_items: int, n_ranks: int, rank: int) -> tuple[int, int]:
     """Contiguous chunk of ceil(N / n_ranks) items per rank (reference gpu:154,169-174)."""
     per = -(-n_items // n_ranks) if n_items > 0 else 0
@@ -46,29 +52,54 @@ def shard_bounds(n_items: int, n_ranks: int, rank: int) -> tuple[int, int]:
     return lo, min(lo + per, n_items)
 
 
-def row_tiles(n_rows: int, n_cols: int, symmetric: bool, n_ranks: int, rank: int, row_block: int = ROW_BLOCK):
-    """Row blocks owned by ``rank`` as [r0, r1, c0, c1] tiles.
+def panel_tiles(n_x: int, n_y: int, symmetric: bool, n_ranks: int, rank: int):
+    """Gram work of ``rank`` as [r0, r1, c0, c1] tiles (rows = y, columns = x).
 
-    Symmetric (train) Gram: only x <= y is computed, so row block b costs ~ (b+1) units; blocks are
-    dealt in a boustrophedon (0..R-1, R-1..0, ...) order, which balances the triangle to within one
-    block per rank.  Rectangular Gram: plain cyclic deal.
+    Every rank owns the rows of its own shard (the Y shard; the X shard for the symmetric train Gram), so its
+    results form one row panel and the matrix is assembled by a gather of panels -- no dense reduce.
+
+    * ``local``: the block of its own rows against its own column shard -- needs no state of another rank, so it
+      runs while the exchange is in flight.  Symmetric: only x <= y inside it, mirrored by the kernel.
+    * ``remote``: the other column shards.  Rectangular Gram: all of them.  Symmetric Gram: the reference's ring
+      schedule (gpu:330-334): column shards r-1, .., r-floor(n/2) (cyclic), all pairs of each block; for an even
+      number of ranks the block at distance n/2 is shared with the partner rank (lower rank: first half of its
+      own rows x the partner's columns; higher rank: its rows x second half of the partner's rows as columns).
+      The matrix entry (y, x) of such a block is stored at [y, x] only; the caller mirrors with max(K, K^T).
+    Every unordered pair is computed exactly once.
     """
-    tiles = []
-    n_blocks = -(-n_rows // row_block)
-    for b in range(n_blocks):
-        rnd, pos = divmod(b, n_ranks)
-        owner = pos if (rnd % 2 == 0 or not symmetric) else n_ranks - 1 - pos
-        if owner != rank:
+    if symmetric:
+        n_y = n_x
+    lo, hi = shard_bounds(n_y, n_ranks, rank)
+    out = {"rows": (lo, hi), "local": [], "remote": []}
+    if hi <= lo:
+        return out
+    if not symmetric:
+        xlo, xhi = shard_bounds(n_x, n_ranks, rank)
+        if xhi > xlo:
+            out["local"].append([lo, hi, xlo, xhi])
+        if xlo > 0:
+            out["remote"].append([lo, hi, 0, xlo])
+        if xhi < n_x:
+            out["remote"].append([lo, hi, xhi, n_x])
+        return out
+    out["local"].append([lo, hi, lo, hi])
+    for k in range(1, n_ranks // 2 + 1):
+        j = (rank - k) % n_ranks
+        clo, chi_ = shard_bounds(n_x, n_ranks, j)
+        if chi_ <= clo:
             continue
-        r0, r1 = b * row_block, min((b + 1) * row_block, n_rows)
-        c1 = min(r1, n_cols) if symmetric else n_cols
-        if tiles and tiles[-1][1] == r0:
-            # contiguous with the previous block of this rank (always, on one rank): one larger tile, so that the
-            # L2 supertiles of qk_gram_frags can block over rows as well as columns
-            tiles[-1][1], tiles[-1][3] = r1, c1
+        if n_ranks % 2 == 0 and k == n_ranks // 2:
+            if rank < j:      # lower rank of the pair: first half of its own rows
+                mid = lo + (hi - lo + 1) // 2
+                if mid > lo:
+                    out["remote"].append([lo, mid, clo, chi_])
+            else:             # higher rank: all its rows x the partner's second half
+                mid = clo + (chi_ - clo + 1) // 2
+                if chi_ > mid:
+                    out["remote"].append([lo, hi, mid, chi_])
         else:
-            tiles.append([r0, r1, 0, c1])
-    return tiles
+            out["remote"].append([lo, hi, clo, chi_])
+    return out
 
 
 class SingleComm:
@@ -88,11 +119,16 @@ def _torch():
     return torch
 
 
-# bond caps tried in turn; each has its own kernel configuration: <= 32 shared-memory-resident kernels (one CTA or, in
-# B form, one small cluster per datapoint), above that the large-matrix kernel (theta in L2, block Jacobi, one CTA
-# cluster per datapoint -- BASELINE config 4)
-CAP_LADDER = (4, 8, 16, 24, 32, 64, 128, 256)
-FRAG_D_LIMIT = 32    # padded bond dimension up to which stage 2 runs on the packed-fragment kernels
+def bond_caps(n_qubits: int, chi_cap: int) -> np.ndarray:
+    """Per-bond caps of a plan: min(chi_cap, chain-edge bound 2^min(b, n-b)) (qk_plan.cpp)."""
+    b = np.arange(n_qubits + 1)
+    e = np.minimum(b, n_qubits - b)
+    return np.minimum(chi_cap, 2 ** np.minimum(e, 30)).astype(np.int32)
+
+
+def store_bytes(n_qubits: int, chi_cap: int) -> int:
+    c = bond_caps(n_qubits, chi_cap).astype(np.int64)
+    return int((c[:-1] * 2 * c[1:]).sum() * 16)
 
 
 class ShardStates:
@@ -106,6 +142,7 @@ class ShardStates:
         self.launches = 0
         self.cap = 1
         self.schedule = ""
+        self.plan = None
 
     def add(self, batch, info, ok_in_batch, shard_pos):
         self.parts.append((batch, info, np.asarray(ok_in_batch, dtype=np.int64), np.asarray(shard_pos, dtype=np.int64)))
@@ -113,8 +150,11 @@ class ShardStates:
     def info(self):
         n, N = self.n_qubits, self.n_local
         out = dict(chi=np.ones((N, n + 1), dtype=np.int32), fidelity=np.ones(N), trunc_weight=np.zeros(N),
-                   nbytes=np.zeros(N, dtype=np.int64), flags=np.zeros(N, dtype=np.int32), sweeps=np.zeros(N, dtype=np.int32))
-        for _, info, ok, pos in self.parts:
+                   nbytes=np.zeros(N, dtype=np.int64), flags=np.zeros(N, dtype=np.int32), sweeps=np.zeros(N, dtype=np.int32),
+                   seconds=np.zeros(N))
+        for batch, info, ok, pos in self.parts:
+            if "seconds" not in info:
+                info["seconds"] = batch.unit_seconds()
             for k in out:
                 out[k][pos] = info[k][ok]
         return out
@@ -126,17 +166,18 @@ class ShardStates:
                 m = np.maximum(m, info["chi"][ok].max(axis=0))
         return m
 
-    def pack(self, D, frag_ptr, stream):
+    def pack(self, D, frag_ptr, first_index, stream):
+        """All valid states into the frag buffer at positions first_index + shard position."""
         for batch, _, ok, pos in self.parts:
             if not len(ok):
                 continue
             dst = np.full(batch.N, -1, dtype=np.int32)
-            dst[ok] = pos
+            dst[ok] = first_index + pos
             batch.pack_scatter(D, frag_ptr, dst, stream)
             self.launches += 1
 
     def single_batch(self):
-        """The batch, if one batch holds every state of the shard in shard order (CUDA-core Gram fallback)."""
+        """The batch, if one batch holds every state of the shard in shard order."""
         if len(self.parts) == 1:
             b, _, ok, pos = self.parts[0]
             if b.N == self.n_local and np.array_equal(ok, pos) and np.array_equal(ok, np.arange(self.n_local)):
@@ -144,23 +185,32 @@ class ShardStates:
         return None
 
 
+def _use_parallel(comm, n_local):
+    env = os.environ.get("QK_SCHEDULE", "")
+    return (env == "parallel") or (env == "" and comm.Get_size() > 1 and 0 < n_local <= PARALLEL_MAX_LOCAL)
+
+
+def _to_device(X_shard, device, n_qubits, torch):
+    if isinstance(X_shard, torch.Tensor):
+        return X_shard.contiguous()
+    if len(X_shard):
+        return torch.from_numpy(np.ascontiguousarray(X_shard, dtype=np.float64)).to(f"cuda:{device}", non_blocking=False)
+    return torch.empty((0, n_qubits), device=f"cuda:{device}", dtype=torch.float64)
+
+
 def _simulate_shard(plan_factory, X_shard, device, chi_cap, comm, n_qubits, escalate=True):
     """Stage 1 on this rank's shard with per-datapoint bond-cap escalation.
 
     ``chi_cap`` is the first cap tried (structural bound, clipped, or the user's ``chi``).  Bond dimensions
     are data dependent (SURVEY.md hard part 1): the shard is simulated with ``QK_PLAN_EARLY_EXIT`` (a datapoint
-    stops at its first cap hit) and only the datapoints that hit the cap are re-run at the next cap of
-    ``CAP_LADDER``.  (Starting below the structural bound does not pay: at small bond dimension the kernel is
-    bound by the per-op latency of one datapoint, not by its shared-memory footprint -- measured, DESIGN.md.)
+    stops at its first cap hit) and only the datapoints that hit the cap are re-run at the next cap.  Up to 32 the
+    caps of ``CAP_LADDER`` are tried one by one (each has its own shared-memory kernel configuration); above 32 the
+    large-matrix kernel works on the actual matrix sizes, so a generous cap costs memory, not time, and the ladder
+    jumps to the largest cap whose working store fits ``BIG_STORE_BUDGET``.
     ``X_shard``: host numpy array (copied through pinned memory) or CUDA tensor.
     """
     torch = _torch()
-    if isinstance(X_shard, torch.Tensor):
-        xt = X_shard.contiguous()
-    elif len(X_shard):
-        xt = torch.from_numpy(np.ascontiguousarray(X_shard, dtype=np.float64)).to(f"cuda:{device}")
-    else:
-        xt = torch.empty((0, n_qubits), device=f"cuda:{device}", dtype=torch.float64)
+    xt = _to_device(X_shard, device, n_qubits, torch)
     torch.cuda.current_stream().synchronize()
     n_local = int(xt.shape[0])
     states = ShardStates(n_local, n_qubits)
@@ -173,13 +223,11 @@ def _simulate_shard(plan_factory, X_shard, device, chi_cap, comm, n_qubits, esca
     # datapoint's op chain.  They run in B form with a cluster of CTAs per datapoint (QK_PLAN_PARALLEL): the
     # dependency depth of the circuit replaces its op count.  Large shards keep the sequential fused schedule,
     # which is throughput-bound anyway (1000 CTAs per 125 datapoints already saturate the SMs).
-    env = os.environ.get("QK_SCHEDULE", "")
-    parallel = (env == "parallel") or (env == "" and comm.Get_size() > 1 and 0 < n_local <= PARALLEL_MAX_LOCAL)
-
+    parallel = _use_parallel(comm, n_local)
     states.schedule = "parallel (B form, one CTA cluster per datapoint)" if parallel else "sequential (one CTA per datapoint)"
 
     def run(cap, idx, early):
-        plan = plan_factory(cap, early, True) if parallel else plan_factory(cap, early)
+        plan = plan_factory(cap, early, True) if (parallel and cap <= 32) else plan_factory(cap, early)
         sub = xt if len(idx) == n_local and np.array_equal(idx, np.arange(n_local)) else xt[torch.from_numpy(idx).to(xt.device)]
         batch = simulate_dev(plan, sub.data_ptr(), int(sub.shape[0]), int(sub.shape[1]), device=device, stream=stream)
         info = batch.info()
@@ -195,8 +243,15 @@ def _simulate_shard(plan_factory, X_shard, device, chi_cap, comm, n_qubits, esca
     level = 0
     while len(pending):
         cap = ladder[level]
+        if cap > 32:
+            # large-matrix kernel: jump to the largest cap whose store fits the budget
+            while level + 1 < len(ladder) and len(pending) * store_bytes(n_qubits, ladder[level + 1]) <= BIG_STORE_BUDGET:
+                level += 1
+            cap = ladder[level]
         last = (level == len(ladder) - 1) or not escalate
         states.cap = max(states.cap, cap)
+        if cap > 32:
+            states.schedule = "large-matrix kernel (one CTA cluster per datapoint, theta in L2, block Jacobi)"
         pending = run(cap, pending, not last)
         if last and len(pending):
             raise QkError(-3, f"bond dimension exceeds the limit of the stage-1 kernels (chi <= {CHI_LIMIT})")
@@ -206,21 +261,193 @@ def _simulate_shard(plan_factory, X_shard, device, chi_cap, comm, n_qubits, esca
     return states
 
 
-def build_gram(comm, plan_factory, n_qubits, X, Y=None, chi_cap=16, device=None, return_device=False):
+def _as_torch_comm(comm):
+    """Multi-rank runs go through torch.distributed; an mpi4py-like communicator is used to bootstrap it."""
+    from .comm import TorchComm, init_from_comm
+    if comm.Get_size() == 1 or isinstance(comm, TorchComm):
+        return comm
+    return init_from_comm(comm)
+
+
+def _gather_panels(comm, panel, n_rows, n_cols, per_rows, symmetric, torch):
+    """Assemble K on rank 0 from the row panels [per_rows, n_cols] of every rank (replaces reduce(SUM), gpu:428)."""
+    from .comm import gather_to_root
+    rank, size = comm.Get_rank(), comm.Get_size()
+    if size == 1:
+        K = panel[:n_rows]
+    else:
+        full = gather_to_root(comm, panel)
+        if rank != 0:
+            return None
+        K = full.view(size * per_rows, n_cols)[:n_rows]
+    if symmetric:
+        K = torch.maximum(K, K.t())     # blocks at cyclic distance >= 1 were stored at [y, x] only; entries are >= 0
+    return K
+
+
+def build_gram(comm, plan_factory, n_qubits, X, Y=None, chi_cap=16, device=None, return_device=False,
+               structural_cap=False):
     """Full path.  Returns (K on rank 0 / None elsewhere, profile dict).
 
     ``X`` / ``Y``: host numpy arrays, or CUDA float64 tensors already resident in HBM (every rank
     holds the full arrays, as in the reference).  ``return_device`` leaves K on the GPU (rank 0).
+    ``structural_cap``: ``chi_cap`` is at least the structural bound of the ansatz, so no state can ask for more:
+    the whole step is then queued without a host round trip (streamlined mode).
     """
     torch = _torch()
-    from .comm import allgather_bytes, allreduce_max_array, reduce_sum_to_root
+    comm = _as_torch_comm(comm)
     rank, size = comm.Get_rank(), comm.Get_size()
     if device is None:
         device = rank % torch.cuda.device_count()   # reference gpu:152
     torch.cuda.set_device(device)
-    dev = f"cuda:{device}"
     if not isinstance(X, torch.Tensor):
         X = np.asarray(X, dtype=np.float64)
+    if Y is not None and not isinstance(Y, torch.Tensor):
+        Y = np.asarray(Y, dtype=np.float64)
+    streamlined = (structural_cap and 4 < chi_cap <= DMMA_D_LIMIT and os.environ.get("QK_ENGINE", "") != "general"
+                   and os.environ.get("QK_GRAM_BIG", "0") != "1")
+    if streamlined:
+        return _build_gram_streamlined(comm, plan_factory, n_qubits, X, Y, chi_cap, device, return_device, torch)
+    return _build_gram_general(comm, plan_factory, n_qubits, X, Y, chi_cap, device, return_device, torch)
+
+
+def _tile_clock_stats(clk, used, torch, device):
+    """Per-inner-product seconds from the per-CTA-tile clocks of the tensor-core kernel (8 pairs per tile)."""
+    if clk is None or used <= 0:
+        return None
+    ticks = clk[:used].cpu().numpy().astype(np.float64)
+    ticks = ticks[ticks > 0]
+    if not len(ticks):
+        return None
+    hz = 1e3 * getattr(torch.cuda.get_device_properties(device), "clock_rate", 1.965e6)
+    return ticks / hz / 8.0
+
+
+def _build_gram_streamlined(comm, plan_factory, n_qubits, X, Y, chi_cap, device, return_device, torch):
+    """No state can exceed ``chi_cap``: stage 1 -> pack -> [all-gather on a side stream || local block] -> remote
+    blocks -> gather of panels, all queued on the device without a host synchronisation in between."""
+    from .comm import allgather_into
+    rank, size = comm.Get_rank(), comm.Get_size()
+    dev = f"cuda:{device}"
+    symmetric = Y is None
+    Nx = len(X)
+    Ny = Nx if symmetric else len(Y)
+    nb = n_qubits + 1
+    t_all = time.perf_counter()
+    main = torch.cuda.current_stream()
+    stream = main.cuda_stream
+    prof = {}
+
+    lo, hi = shard_bounds(Nx, size, rank)
+    parallel = _use_parallel(comm, hi - lo)
+    plan = plan_factory(chi_cap, False, True) if parallel else plan_factory(chi_cap, False)
+    D = pad_dims(bond_caps(n_qubits, chi_cap))
+    stride = frag_stride(n_qubits, D)
+    per_x = -(-Nx // size)
+    fragX = torch.empty(size * max(per_x, 1) * stride, dtype=torch.uint8, device=dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    xt = _to_device(X[lo:hi], device, n_qubits, torch)
+    bx = simulate_async(plan, xt.data_ptr(), int(xt.shape[0]), int(xt.shape[1]) if xt.shape[0] else n_qubits,
+                        device=device, stream=stream)
+    bx.pack_async(D, fragX.data_ptr(), rank * per_x, stream)
+    launches = 2
+    by, fragY, ylo, yhi = None, None, lo, hi
+    if not symmetric:
+        ylo, yhi = shard_bounds(Ny, size, rank)
+        yt = _to_device(Y[ylo:yhi], device, n_qubits, torch)
+        by = simulate_async(plan, yt.data_ptr(), int(yt.shape[0]), int(yt.shape[1]) if yt.shape[0] else n_qubits,
+                            device=device, stream=stream)
+        fragY = torch.empty(max(yhi - ylo, 1) * stride, dtype=torch.uint8, device=dev)   # bras are only needed locally
+        by.pack_async(D, fragY.data_ptr(), 0, stream)
+        launches += 2
+    gathered = None
+    if size > 1:
+        packed = torch.cuda.Event()
+        packed.record(main)
+        side = torch.cuda.Stream(device=device)
+        side.wait_event(packed)
+        with torch.cuda.stream(side):
+            allgather_into(comm, fragX, rank * per_x * stride, per_x * stride)
+            gathered = torch.cuda.Event()
+            gathered.record(side)
+
+    work = panel_tiles(Nx, Ny, symmetric, size, rank)
+    per_rows = -(-Ny // size)
+    panel = torch.zeros((max(per_rows, 1), Nx), dtype=torch.float64, device=dev)
+    k_ptr = panel.data_ptr() - work["rows"][0] * Nx * 8          # the kernels index rows globally
+    fy_ptr = None if symmetric else fragY.data_ptr() - ylo * stride
+    n_tiles_max = ((per_rows + 1) // 2 + 2) * ((Nx + 3) // 4 + 2)
+    clk = torch.zeros(n_tiles_max, dtype=torch.int64, device=dev) if size == 1 and os.environ.get("QK_TILE_CLOCKS", "1") != "0" else None
+    ev[0].record(main)
+    if work["local"]:
+        # the local block reads only this rank's states: it runs while the all-gather is in flight
+        gram_frags(device, n_qubits, D, fragX.data_ptr(), hi, None if symmetric else D, fy_ptr, yhi,
+                   work["local"], symmetric, k_ptr, Nx, stream, wait=False,
+                   tile_clocks=(clk.data_ptr(), n_tiles_max) if clk is not None else None)
+        launches += 1
+    ev[1].record(main)
+    if gathered is not None:
+        main.wait_event(gathered)
+    ev[2].record(main)
+    if work["remote"]:
+        gram_frags(device, n_qubits, D, fragX.data_ptr(), Nx, D, fragX.data_ptr() if symmetric else fy_ptr,
+                   Nx if symmetric else yhi, work["remote"], False, k_ptr, Nx, stream, wait=False)
+        launches += 1
+    ev[3].record(main)
+    K = _gather_panels(comm, panel, Ny, Nx, max(per_rows, 1), symmetric, torch)
+    out = None
+    if rank == 0:
+        out = K if return_device else K.cpu().numpy()
+    torch.cuda.synchronize()
+
+    info_x = bx.info()
+    info_x["seconds"] = bx.unit_seconds()
+    info_y = None
+    if by is not None:
+        info_y = by.info()
+        info_y["seconds"] = by.unit_seconds()
+    for inf in (info_x, info_y):
+        if inf is not None and len(inf["flags"]):
+            if np.any(inf["flags"] & QK_FLAG_NO_CONVERGE):
+                raise QkError(-2, "stage 1: the Jacobi SVD hit its sweep limit on at least one state")
+            if np.any(inf["flags"] & QK_FLAG_CAP_HIT):
+                raise QkError(-3, "a state exceeded a bond cap that was declared structural")
+    prof["sim_ms_x"] = bx.sim_ms()
+    prof["sim_ms_y"] = by.sim_ms() if by is not None else 0.0
+    prof["chi_cap"] = chi_cap
+    prof["info_x"], prof["info_y"] = info_x, info_y
+    prof["plan"] = plan.info()
+    prof["plan_obj"] = plan
+    prof["stage1_schedule"] = ("parallel (B form, one CTA cluster per datapoint)" if parallel
+                               else "sequential (one CTA per datapoint)")
+    prof["shard"] = (lo, hi)
+    prof["gram_kernel"] = "qk_gram_dmma_kernel"
+    prof["gram_ms_local"] = ev[0].elapsed_time(ev[1])
+    prof["gram_ms_remote"] = ev[2].elapsed_time(ev[3])
+    prof["gram_ms"] = prof["gram_ms_local"] + prof["gram_ms_remote"]
+    prof["exchange_wait_ms"] = ev[1].elapsed_time(ev[2])      # what the all-gather costs beyond the local block
+    prof["exchange_s"] = prof["exchange_wait_ms"] * 1e-3
+    prof["exchange"] = ("none (one rank)" if size == 1 else
+                        "all-gather of packed states on a side stream, overlapped with the local x local block; "
+                        "row panels gathered to rank 0")
+    prof["frag_bytes_per_state"] = (stride, stride)
+    prof["Dx"], prof["Dy"] = D, D
+    prof["launches"] = launches
+    prof["mode"] = "streamlined"
+    prof["pair_seconds"] = _tile_clock_stats(clk, n_tiles_max, torch, device)
+    prof["no_converge"] = 0
+    prof["total_s"] = time.perf_counter() - t_all
+    return out, prof
+
+
+def _build_gram_general(comm, plan_factory, n_qubits, X, Y, chi_cap, device, return_device, torch):
+    """Data-dependent bond dimensions: stage 1 with cap escalation, then the stage-2 path is chosen from the measured
+    (all-reduced) bond dimensions -- lane-per-pair kernel (chi <= 4), tensor-core fragments (padded D <= 16),
+    CUDA-core fragments (D <= 32) or batched GEMMs on the stores (any chi)."""
+    from .comm import allgather_bytes, allreduce_max_array
+    rank, size = comm.Get_rank(), comm.Get_size()
+    dev = f"cuda:{device}"
     symmetric = Y is None
     Nx = len(X)
     Ny = Nx if symmetric else len(Y)
@@ -232,14 +459,12 @@ def build_gram(comm, plan_factory, n_qubits, X, Y=None, chi_cap=16, device=None,
     # rank-local and data dependent: it is carried through the collective below and raised on EVERY rank, so that
     # the other ranks do not block forever in all_reduce / all_gather.
     lo, hi = shard_bounds(Nx, size, rank)
-    sy, info_y, local_err = None, None, None
+    ylo, yhi = (lo, hi) if symmetric else shard_bounds(Ny, size, rank)
+    sx, sy, info_x, info_y, local_err = None, None, None, None, None
     try:
         sx = _simulate_shard(plan_factory, X[lo:hi], device, chi_cap, comm, n_qubits)
         info_x = sx.info()
         if not symmetric:
-            if not isinstance(Y, torch.Tensor):
-                Y = np.asarray(Y, dtype=np.float64)
-            ylo, yhi = shard_bounds(Ny, size, rank)
             sy = _simulate_shard(plan_factory, Y[ylo:yhi], device, chi_cap, comm, n_qubits)
             info_y = sy.info()
         for inf in (info_x, info_y):
@@ -263,10 +488,10 @@ def build_gram(comm, plan_factory, n_qubits, X, Y=None, chi_cap=16, device=None,
     prof["stage1_schedule"] = sx.schedule
     prof["plan_obj"] = sx.plan
     prof["shard"] = (lo, hi)
+    prof["mode"] = "general"
 
-    # ---- exchange: batch-uniform padded dims, pack, all-gather
+    # ---- exchange: one collective for the per-bond maxima, "plain batch" flag and the common bond cap
     t0 = time.perf_counter()
-    # one collective for the per-bond maxima and for "every rank holds its shard as one plain batch"
     lane_local = sx.single_batch() is not None or sx.n_local == 0
     if not symmetric:
         lane_local = lane_local and (sy.single_batch() is not None or sy.n_local == 0) and \
@@ -281,108 +506,122 @@ def build_gram(comm, plan_factory, n_qubits, X, Y=None, chi_cap=16, device=None,
     use_lane = (max_chi <= LANE_CHI_LIMIT and int(red[-2]) == 0 and os.environ.get("QK_GRAM_LANE", "1") != "0")
     use_big = (not use_lane) and (int(max(Dx.max(), Dy.max())) > FRAG_D_LIMIT or os.environ.get("QK_GRAM_BIG", "0") == "1")
     stream = torch.cuda.current_stream().cuda_stream
-    K = torch.zeros((Ny, Nx), dtype=torch.float64, device=dev)
-    tiles = row_tiles(Ny, Nx, symmetric, size, rank)
+    work = panel_tiles(Nx, Ny, symmetric, size, rank)
+    per_x, per_rows = -(-Nx // size), -(-Ny // size)
+    panel = torch.zeros((max(per_rows, 1), Nx), dtype=torch.float64, device=dev)
+    k_ptr = panel.data_ptr() - work["rows"][0] * Nx * 8          # the kernels index rows globally
     ms = 0.0
+    prof["exchange"] = "none (one rank)" if size == 1 else "all-gather of the ket states; bras stay local; row panels gathered to rank 0"
 
-    if use_lane:
-        # bond dimensions <= 4: the unpadded stores themselves are exchanged and read by the lane-per-pair kernel
-        prof["gram_kernel"] = "qk_gram_lane_kernel"
-        plan = sx.plan
+    def launches_for(run):
+        """local block (x <= y mirrored when symmetric), then the remote blocks (all pairs, stored at [y, x] only)"""
+        t = 0.0
+        if work["local"]:
+            t += run(work["local"], symmetric, True)
+        if work["remote"]:
+            t += run(work["remote"], False, False)
+        return t
+
+    if use_lane or use_big:
+        # the unpadded stores themselves (+ bond dimensions) are exchanged
+        if use_lane:
+            prof["gram_kernel"] = "qk_gram_lane_kernel"
+            plan = sx.plan
+        else:
+            # every rank re-lays its states out for the common bond cap (shards may have escalated differently)
+            prof["gram_kernel"] = "qk_big_gemm_kernel"
+            plan = plan_factory(cap_common, False)
         stride_b = int(plan.info().state_stride) * 16
 
-        def gathered(shard, n_total):
+        def stores(shard, n_total, gather):
+            """(store ptr, chi ptr, keep-alive) addressed by GLOBAL state index"""
+            first = shard_bounds(n_total, size, rank)[0]
             b = shard.single_batch()
-            if size == 1:
+            if use_lane and size == 1:
                 ptr, _, chi_ptr = b.store()
                 return ptr, chi_ptr, None
             per = -(-n_total // size)
-            st = torch.zeros(max(per, 1) * stride_b, dtype=torch.uint8, device=dev)
-            ch = torch.ones(max(per, 1) * nb, dtype=torch.int32, device=dev)
-            if b is not None and b.N:
-                ptr, _, chi_ptr = b.store()
-                st[:b.N * stride_b].copy_(torch.as_tensor(_DevView(ptr, b.N * stride_b), device=dev))
-                ch[:b.N * nb].copy_(torch.as_tensor(_DevView(chi_ptr, b.N * nb * 4), device=dev).view(torch.int32))
-            st_all, ch_all = allgather_bytes(comm, st), allgather_bytes(comm, ch)
-            return st_all.data_ptr(), ch_all.data_ptr(), (st_all, ch_all)
+            n_slots = size * max(per, 1) if gather else max(shard.n_local, 1)
+            base = rank * per if gather else 0
+            st = torch.empty(n_slots * stride_b, dtype=torch.uint8, device=dev)
+            ch = torch.ones(n_slots * nb, dtype=torch.int32, device=dev)
+            if use_lane:
+                if b is not None and b.N:
+                    ptr, _, chi_ptr = b.store()
+                    st[base * stride_b:(base + b.N) * stride_b].copy_(torch.as_tensor(_DevView(ptr, b.N * stride_b), device=dev))
+                    ch[base * nb:(base + b.N) * nb].copy_(torch.as_tensor(_DevView(chi_ptr, b.N * nb * 4), device=dev).view(torch.int32))
+            else:
+                for batch, _, ok, pos in shard.parts:
+                    if len(ok):
+                        dst = np.full(batch.N, -1, dtype=np.int32)
+                        dst[ok] = base + pos
+                        batch.repack(plan, st.data_ptr(), ch.data_ptr(), dst, stream)
+                        shard.launches += 1
+            if gather and size > 1:
+                from .comm import allgather_into
+                allgather_into(comm, st, rank * per * stride_b, per * stride_b)
+                allgather_into(comm, ch.view(torch.uint8), rank * per * nb * 4, per * nb * 4)
+                return st.data_ptr(), ch.data_ptr(), (st, ch)
+            off = 0 if gather else first
+            return st.data_ptr() - off * stride_b, ch.data_ptr() - off * nb * 4, (st, ch)
 
-        px, cx, keep_x = gathered(sx, Nx)
-        py, cy, keep_y = (px, cx, None) if symmetric else gathered(sy, Ny)
+        px, cx, keep_x = stores(sx, Nx, True)
+        py, cy, keep_y = (px, cx, None) if symmetric else stores(sy, Ny, False)
         torch.cuda.synchronize()
         prof["exchange_s"] = time.perf_counter() - t0
         prof["frag_bytes_per_state"] = (stride_b, stride_b)
-        if tiles:
-            ms = gram_lane(plan, device, max_chi, px, cx, Nx, None if symmetric else py, None if symmetric else cy, Ny,
-                           tiles, symmetric, K.data_ptr(), Nx, stream)
-            launches += 1
-        del keep_x, keep_y
-    elif use_big:
-        # bond dimensions above the fragment kernels (BASELINE config 4): every rank re-lays its states out for the
-        # common bond cap, the unpadded stores + bond dimensions are exchanged, and the transfer sweep runs as
-        # batched complex GEMMs on the FP64 tensor cores
-        prof["gram_kernel"] = "qk_big_gemm_kernel"
-        plan = plan_factory(cap_common, False)
-        stride_b = int(plan.info().state_stride) * 16
 
-        def relaid(shard, n_total):
-            per = -(-n_total // size)
-            st = torch.empty(max(per, 1) * stride_b, dtype=torch.uint8, device=dev)
-            ch = torch.ones(max(per, 1) * nb, dtype=torch.int32, device=dev)
-            for batch, _, ok, pos in shard.parts:
-                if len(ok):
-                    dst = np.full(batch.N, -1, dtype=np.int32)
-                    dst[ok] = pos
-                    batch.repack(plan, st.data_ptr(), ch.data_ptr(), dst, stream)
-                    shard.launches += 1
-            if size == 1:
-                return st, ch
-            return allgather_bytes(comm, st), allgather_bytes(comm, ch)
-
-        stx, chx = relaid(sx, Nx)
-        sty, chy = (stx, chx) if symmetric else relaid(sy, Ny)
-        torch.cuda.synchronize()
-        prof["exchange_s"] = time.perf_counter() - t0
-        prof["frag_bytes_per_state"] = (stride_b, stride_b)
-        if tiles:
-            ms = gram_big(plan, device, red[:nb], None if symmetric else red[nb:2 * nb], stx.data_ptr(), chx.data_ptr(), Nx,
-                          None if symmetric else sty.data_ptr(), None if symmetric else chy.data_ptr(), Ny, tiles,
-                          symmetric, K.data_ptr(), Nx, stream)
+        def run(tiles, sym, is_local):
+            nonlocal launches
+            ny_arg = Nx if symmetric else yhi
+            if use_lane:
+                launches += 1
+                return gram_lane(plan, device, max_chi, px, cx, Nx, None if sym else py, None if sym else cy, ny_arg,
+                                 tiles, sym, k_ptr, Nx, stream)
             launches += 2 * n_qubits + 2
-        del stx, chx, sty, chy
+            return gram_big(plan, device, red[:nb], None if sym else red[(0 if symmetric else nb):(nb if symmetric else 2 * nb)],
+                            px, cx, Nx, None if sym else py, None if sym else cy, ny_arg, tiles, sym, k_ptr, Nx, stream)
+
+        ms = launches_for(run)
+        del keep_x, keep_y
     else:
         prof["gram_kernel"] = "qk_gram_dmma_kernel" if int(max(Dx.max(), Dy.max())) <= DMMA_D_LIMIT else \
             "qk_gram_frag_generic_kernel"   # D > 16: CUDA-core kernel on the same packed buffers (any rank count)
-
-        def packed(shard, D, n_total):
-            stride = frag_stride(n_qubits, D)
-            per = -(-n_total // size)
-            local = torch.empty(max(per, 1) * stride, dtype=torch.uint8, device=dev)
-            shard.pack(D, local.data_ptr(), stream)
-            if size == 1:
-                return local, stride
-            return allgather_bytes(comm, local), stride
-
-        fx, stride_x = packed(sx, Dx, Nx)
-        fy, stride_y = (fx, stride_x) if symmetric else packed(sy, Dy, Ny)
+        stride_x = frag_stride(n_qubits, Dx)
+        fx = torch.empty(size * max(per_x, 1) * stride_x, dtype=torch.uint8, device=dev)
+        sx.pack(Dx, fx.data_ptr(), rank * per_x, stream)
+        if size > 1:
+            from .comm import allgather_into
+            allgather_into(comm, fx, rank * per_x * stride_x, per_x * stride_x)
+        stride_y, fy_ptr = stride_x, fx.data_ptr()
+        fy = None
+        if not symmetric:
+            stride_y = frag_stride(n_qubits, Dy)
+            fy = torch.empty(max(sy.n_local, 1) * stride_y, dtype=torch.uint8, device=dev)    # bras are only needed locally
+            sy.pack(Dy, fy.data_ptr(), 0, stream)
+            fy_ptr = fy.data_ptr() - ylo * stride_y
         torch.cuda.synchronize()
         prof["exchange_s"] = time.perf_counter() - t0
         prof["frag_bytes_per_state"] = (stride_x, stride_y)
 
-        # ---- stage 2 on this rank's row blocks
-        if tiles:
-            ms = gram_frags(device, n_qubits, Dx, fx.data_ptr(), Nx, None if symmetric else Dy,
-                            None if symmetric else fy.data_ptr(), Ny, tiles, symmetric, K.data_ptr(), Nx, stream)
+        def run(tiles, sym, is_local):
+            nonlocal launches
             launches += 1
+            return gram_frags(device, n_qubits, Dx, fx.data_ptr(), Nx, None if sym else Dy, None if sym else fy_ptr,
+                              Nx if symmetric else yhi, tiles, sym, k_ptr, Nx, stream)
+
+        ms = launches_for(run)
+        del fy
     launches += sx.launches + (sy.launches if sy is not None else 0)
     prof["gram_ms"] = ms
     prof["Dx"], prof["Dy"] = Dx, Dy
     prof["launches"] = launches
-    if size > 1:
-        K = reduce_sum_to_root(comm, K)
+    K = _gather_panels(comm, panel, Ny, Nx, max(per_rows, 1), symmetric, torch)
     out = None
     if rank == 0:
         out = K if return_device else K.cpu().numpy()
     torch.cuda.synchronize()
+    prof["pair_seconds"] = None
     prof["total_s"] = time.perf_counter() - t_all
     prof["no_converge"] = 0   # a sweep-limit hit raises above (on every rank)
     return out, prof

@@ -169,7 +169,7 @@ def test_plan_errors(qk):
     with pytest.raises(RuntimeError):
         qk.Plan(4, [("CX", (0, 1), None)], 0, 1e-16, 4)                     # unknown gate (cpu:129)
     with pytest.raises(qk.QkError) as e:
-        qk.Plan(4, [("H", (0,), None)], 0, 1e-16, 512)                      # above the limit of the stage-1 kernels
+        qk.Plan(4, [("H", (0,), None)], 0, 1e-16, 1024)                     # above the limit of the stage-1 kernels
     assert e.value.code == qk.QK_ERR_LIMIT
     big = qk.Plan(4, [("H", (0,), None)], 0, 1e-16, 64)                     # above 32: the large-matrix kernel's plan
     assert big.info().threads == 256 and big.info().chi_cap == 64

@@ -24,25 +24,39 @@ def test_shard_bounds_cover_everything():
 
 
 @pytest.mark.parametrize("symmetric", [True, False])
-def test_row_tiles_partition(symmetric):
-    from qkmps.engine import row_tiles
-    for rows, cols in [(1, 1), (13, 13), (40, 40), (100, 100), (1000, 1000)] + ([] if symmetric else [(8, 40), (37, 100)]):
-        for size in (1, 2, 4, 8):
+def test_panel_tiles_partition(symmetric):
+    """Every (unordered, if symmetric) pair is computed by exactly one rank; rows stay inside the rank's own panel;
+    the local block needs only the rank's own states; work is balanced across ranks."""
+    from qkmps.engine import panel_tiles, shard_bounds
+    shapes = [(1, 1), (13, 13), (40, 40), (100, 100), (1000, 1000)] + ([] if symmetric else [(40, 8), (100, 37), (7, 3)])
+    for cols, rows in shapes:
+        for size in (1, 2, 3, 4, 5, 8):
             cover = np.zeros((rows, cols), dtype=int)
             work = []
             for r in range(size):
-                w = 0
-                for r0, r1, c0, c1 in row_tiles(rows, cols, symmetric, size, r):
-                    for y in range(r0, r1):
-                        xs = range(c0, min(c1, y + 1)) if symmetric else range(c0, c1)
-                        for x in xs:
-                            cover[y, x] += 1
-                            w += 1
-                work.append(w)
-            expect = np.tril(np.ones((rows, cols), dtype=int)) if symmetric else np.ones((rows, cols), dtype=int)
-            assert np.array_equal(cover, expect)
+                w = panel_tiles(cols, rows, symmetric, size, r)
+                lo, hi = w["rows"]
+                assert (lo, hi) == shard_bounds(rows, size, r)
+                n = 0
+                for kind in ("local", "remote"):
+                    for r0, r1, c0, c1 in w[kind]:
+                        assert lo <= r0 <= r1 <= hi and 0 <= c0 <= c1 <= cols
+                        if kind == "local":
+                            xlo, xhi = shard_bounds(cols, size, r)
+                            assert xlo <= c0 and c1 <= xhi
+                        for y in range(r0, r1):
+                            xs = range(c0, min(c1, y + 1)) if (symmetric and kind == "local") else range(c0, c1)
+                            for x in xs:
+                                cover[y, x] += 1
+                                n += 1
+                work.append(n)
+            if symmetric:
+                both = cover + cover.T - np.diag(np.diag(cover))
+                assert np.array_equal(both, np.ones((rows, cols), dtype=int)), (rows, size)
+            else:
+                assert np.array_equal(cover, np.ones((rows, cols), dtype=int))
             if rows >= 1000:
-                assert max(work) <= 1.05 * (sum(work) / size)      # balanced to within one row block
+                assert max(work) <= 1.02 * (sum(work) / size) + 1
 
 
 def _free_port():
@@ -61,9 +75,9 @@ def _worker(rank, world, port, out):
         sys.path.insert(0, str(p))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch
-    from qkmps.comm import (allgather_bytes, allreduce_max_array, allreduce_max_int, init_from_env,
-                            reduce_sum_to_root)
-    from qkmps.engine import row_tiles, shard_bounds
+    from qkmps.comm import (allgather_bytes, allgather_into, allreduce_max_array, allreduce_max_int, gather_to_root,
+                            init_from_env)
+    from qkmps.engine import panel_tiles, shard_bounds
     comm = init_from_env("gloo")
     assert comm.Get_rank() == rank and comm.Get_size() == world
     assert list(allreduce_max_array(comm, np.array([rank + 1, 5 - rank], dtype=np.int32))) == [world, 5]
@@ -86,14 +100,30 @@ def _worker(rank, world, port, out):
             self.tensors = t
     states = [_M(t) for part in gathered for t in part]
     assert len(states) == N
-    K = torch.zeros((N, N), dtype=torch.float64)
-    for r0, r1, c0, c1 in row_tiles(N, N, True, world, rank):
-        for y in range(r0, r1):
-            for x in range(c0, min(c1, y + 1)):
-                v = abs(mps_inner(states[y], states[x])) ** 2
-                K[y, x] = v
-                K[x, y] = v
-    K = reduce_sum_to_root(comm, K)
+    # the engine's assembly: every rank fills its own row panel (global row index through an offset), the panels are
+    # gathered to rank 0 and the symmetric matrix is completed with max(K, K^T)
+    from qkmps.engine import _gather_panels
+    work = panel_tiles(N, N, True, world, rank)
+    per = -(-N // world)
+    panel = torch.zeros((per, N), dtype=torch.float64)
+    row0 = work["rows"][0]
+    for kind in ("local", "remote"):
+        for r0, r1, c0, c1 in work[kind]:
+            for y in range(r0, r1):
+                for x in (range(c0, min(c1, y + 1)) if kind == "local" else range(c0, c1)):
+                    v = abs(mps_inner(states[y], states[x])) ** 2
+                    panel[y - row0, x] = v
+                    if kind == "local":
+                        panel[x - row0, y] = v
+    K = _gather_panels(comm, panel, N, N, per, True, torch)
+    buf = torch.arange(world * 4, dtype=torch.uint8) * 0 + 255
+    buf[rank * 4:(rank + 1) * 4] = rank
+    allgather_into(comm, buf, rank * 4, 4)
+    assert buf.tolist() == sum([[q] * 4 for q in range(world)], [])
+    gr = gather_to_root(comm, torch.full((3,), float(rank)))
+    assert (gr is None) == (rank != 0)
+    if rank == 0:
+        assert gr.tolist() == sum([[float(q)] * 3 for q in range(world)], [])
     red = comm.reduce(np.full((2, 2), float(rank + 1)))
     if rank == 0:
         Kref = gram_from_mps(simulate_batch(n, r, gmm, emap, X))
@@ -106,8 +136,8 @@ def _worker(rank, world, port, out):
     torch.distributed.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2])
-def test_gloo_two_ranks(world):
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_ranks(world):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
