@@ -1,5 +1,5 @@
 """Drop-in for the reference's ``cpu_backend/kernel_state_ansatz.py``: same entry points, arguments,
-return value, side effects (``<info_file>.json``) and profiling keys.  The reference ran this backend
+return value, side effects (``<info_file>.json``, per-rank checkpoint under ``tmp/``) and profiling keys.  The reference ran this backend
 on ITensors.jl through ``KernelPkg.compute_tile``; here the same truncation semantics (ITensors
 relative ``cutoff``, no renormalisation -- cpu:262 -> KernelPkg.jl:68) are served by the sm_100a
 kernels in libqkmps.so.  There is no CPU arithmetic path in this package.
@@ -25,7 +25,7 @@ if _PKG_ROOT not in sys.path:
 from qkmps import QK_PLAN_EARLY_EXIT, QK_PLAN_PARALLEL, QK_TRUNC_ITENSORS, Plan  # noqa: E402
 from qkmps.ansatz import KernelStateAnsatzBase, expected_chi, structural_chi_bound  # noqa: E402
 from qkmps.comm import Wtime  # noqa: E402
-from qkmps.engine import build_gram  # noqa: E402
+from qkmps.engine import Checkpoint, build_gram  # noqa: E402
 
 _KNOWN = ("H", "Rx", "Rz", "XXPhase", "ZZPhase", "SWAP")
 
@@ -46,9 +46,11 @@ def build_kernel_matrix(mpi_comm, ansatz, X, Y=None, info_file="info_file", trun
                         number_of_tiles: Optional[int] = None, chi: Optional[int] = None) -> np.ndarray:
     """Kernel matrix of dimensions ``len(Y) x len(X)`` (``len(X) x len(X)`` when ``Y`` is None).
 
-    ``number_of_tiles`` is accepted for compatibility; it only sets the tile count reported in the
-    profiling JSON (the GPU path deals 8-row blocks of K to the ranks and does not re-simulate
-    circuits per tile, unlike KernelPkg.compute_tile, KernelPkg.jl:81-99).
+    ``number_of_tiles`` (default ``4 * n_procs`` like the reference, cpu:179) sets the tile count reported in the
+    profiling JSON and the granularity of the checkpoint: every rank cuts its rows of K into
+    ``number_of_tiles // n_procs`` row groups and rewrites ``tmp/checkpoint_rank_<rank>_<info_file>.npz`` after each
+    (reference: ``.npy`` after every tile, cpu:212-233,279-282); a restarted run skips the finished groups and the
+    file is deleted on success (cpu:326).  Circuits are simulated once, not once per tile (KernelPkg.jl:81-99).
     """
     n_procs, rank, root = mpi_comm.Get_size(), mpi_comm.Get_rank(), 0
     lenX = len(X)
@@ -81,8 +83,12 @@ def build_kernel_matrix(mpi_comm, ansatz, X, Y=None, info_file="info_file", trun
         cap0 = next((c for c in (4, 8, 16) if est <= c), 16)
     start_time = Wtime()
     bound_s = max(1, structural_chi_bound(ansatz.num_qubits, ansatz.reps, ansatz.entanglement_map))
+    ckpt = Checkpoint(os.path.join("tmp", f"checkpoint_rank_{rank}_{os.path.basename(str(info_file))}.npz"),
+                      groups=max(1, number_of_tiles // max(n_procs, 1)))
+    build_kernel_matrix.last_checkpoint = ckpt
+    ckpt.abort_after = getattr(build_kernel_matrix, "_abort_after", None)      # tests only
     K, prof = build_gram(mpi_comm, plan_factory, n_qubits, np.asarray(X), None if Y is None else np.asarray(Y),
-                         chi_cap=cap0, structural_cap=(cap0 >= bound_s))
+                         chi_cap=cap0, structural_cap=(cap0 >= bound_s), checkpoint=ckpt)
 
     if rank == root:
         ix, iy = prof["info_x"], prof["info_y"]

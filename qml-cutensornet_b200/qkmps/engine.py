@@ -266,7 +266,9 @@ def _as_torch_comm(comm):
     from .comm import TorchComm, init_from_comm
     if comm.Get_size() == 1 or isinstance(comm, TorchComm):
         return comm
-    return init_from_comm(comm)
+    if hasattr(comm, "as_torch_comm"):       # compat/mpi4py stand-in under torchrun
+        return comm.as_torch_comm()
+    return init_from_comm(comm)                # a real mpi4py communicator: rendezvous through its bcast
 
 
 def _gather_panels(comm, panel, n_rows, n_cols, per_rows, symmetric, torch):
@@ -285,8 +287,45 @@ def _gather_panels(comm, panel, n_rows, n_cols, per_rows, symmetric, torch):
     return K
 
 
+class Checkpoint:
+    """Per-rank checkpoint of the Gram row panel (replaces cpu_backend/kernel_state_ansatz.py:212-233,252-253,279-282,326
+    of the reference: a per-rank ``tmp/checkpoint_rank_<rank>_<info_file>.npy`` rewritten after every tile, a tile
+    counting as done iff its first entry is non-zero).  Here the rank's rows are cut into ``groups`` row groups; after
+    each group the panel and an explicit "done" bitmap are written atomically; a restart loads them, skips the finished
+    groups and the file is removed once the matrix is complete."""
+
+    def __init__(self, path, groups=4):
+        self.path, self.groups = str(path), max(1, int(groups))
+        self.groups_run = 0          # row groups computed by this call (tests)
+        self.abort_after = None      # tests: raise after this many groups were written
+
+    def _sig(self, shape, rows, n_qubits, symmetric, size):
+        return np.array([shape[0], shape[1], rows[0], rows[1], n_qubits, int(symmetric), size, self.groups], dtype=np.int64)
+
+    def load(self, shape, rows, n_qubits, symmetric, size):
+        done = np.zeros(self.groups, dtype=bool)
+        if os.path.exists(self.path):
+            try:
+                z = np.load(self.path)
+                if np.array_equal(z["sig"], self._sig(shape, rows, n_qubits, symmetric, size)) and z["panel"].shape == tuple(shape):
+                    return z["panel"], z["done"].astype(bool)
+            except Exception:   # noqa: BLE001  (unreadable / foreign file: start over)
+                pass
+        return None, done
+
+    def save(self, panel_host, done, rows, n_qubits, symmetric, size):
+        os.makedirs(os.path.dirname(self.path) or ".", exist_ok=True)
+        tmp = self.path + ".part.npz"
+        np.savez(tmp, panel=panel_host, done=done, sig=self._sig(panel_host.shape, rows, n_qubits, symmetric, size))
+        os.replace(tmp, self.path)
+
+    def remove(self):
+        if os.path.exists(self.path):
+            os.remove(self.path)
+
+
 def build_gram(comm, plan_factory, n_qubits, X, Y=None, chi_cap=16, device=None, return_device=False,
-               structural_cap=False):
+               structural_cap=False, checkpoint=None):
     """Full path.  Returns (K on rank 0 / None elsewhere, profile dict).
 
     ``X`` / ``Y``: host numpy arrays, or CUDA float64 tensors already resident in HBM (every rank
@@ -305,10 +344,10 @@ def build_gram(comm, plan_factory, n_qubits, X, Y=None, chi_cap=16, device=None,
     if Y is not None and not isinstance(Y, torch.Tensor):
         Y = np.asarray(Y, dtype=np.float64)
     streamlined = (structural_cap and 4 < chi_cap <= DMMA_D_LIMIT and os.environ.get("QK_ENGINE", "") != "general"
-                   and os.environ.get("QK_GRAM_BIG", "0") != "1")
+                   and os.environ.get("QK_GRAM_BIG", "0") != "1" and checkpoint is None)
     if streamlined:
         return _build_gram_streamlined(comm, plan_factory, n_qubits, X, Y, chi_cap, device, return_device, torch)
-    return _build_gram_general(comm, plan_factory, n_qubits, X, Y, chi_cap, device, return_device, torch)
+    return _build_gram_general(comm, plan_factory, n_qubits, X, Y, chi_cap, device, return_device, torch, checkpoint)
 
 
 def _tile_clock_stats(clk, used, torch, device):
@@ -441,7 +480,7 @@ def _build_gram_streamlined(comm, plan_factory, n_qubits, X, Y, chi_cap, device,
     return out, prof
 
 
-def _build_gram_general(comm, plan_factory, n_qubits, X, Y, chi_cap, device, return_device, torch):
+def _build_gram_general(comm, plan_factory, n_qubits, X, Y, chi_cap, device, return_device, torch, checkpoint=None):
     """Data-dependent bond dimensions: stage 1 with cap escalation, then the stage-2 path is chosen from the measured
     (all-reduced) bond dimensions -- lane-per-pair kernel (chi <= 4), tensor-core fragments (padded D <= 16),
     CUDA-core fragments (D <= 32) or batched GEMMs on the stores (any chi)."""
@@ -514,12 +553,45 @@ def _build_gram_general(comm, plan_factory, n_qubits, X, Y, chi_cap, device, ret
     prof["exchange"] = "none (one rank)" if size == 1 else "all-gather of the ket states; bras stay local; row panels gathered to rank 0"
 
     def launches_for(run):
-        """local block (x <= y mirrored when symmetric), then the remote blocks (all pairs, stored at [y, x] only)"""
+        """local block (x <= y mirrored when symmetric), then the remote blocks (all pairs, stored at [y, x] only);
+        with a checkpoint: one row group of this rank's panel at a time, written to disk after each"""
+        if checkpoint is None:
+            t = 0.0
+            if work["local"]:
+                t += run(work["local"], symmetric, True)
+            if work["remote"]:
+                t += run(work["remote"], False, False)
+            return t
+        r_lo, r_hi = work["rows"]
+        saved, done = checkpoint.load(tuple(panel.shape), (r_lo, r_hi), n_qubits, symmetric, size)
+        if saved is not None:
+            panel.copy_(torch.from_numpy(saved).to(dev))
+        step = -(-max(r_hi - r_lo, 1) // checkpoint.groups)
         t = 0.0
-        if work["local"]:
-            t += run(work["local"], symmetric, True)
-        if work["remote"]:
-            t += run(work["remote"], False, False)
+        for g in range(checkpoint.groups):
+            g0, g1 = r_lo + g * step, min(r_lo + (g + 1) * step, r_hi)
+            if done[g] or g1 <= g0:
+                done[g] = True
+                continue
+
+            def clip(tiles):
+                out = []
+                for r0, r1, c0, c1 in tiles:
+                    a, b = max(r0, g0), min(r1, g1)
+                    if b > a and c1 > c0:
+                        out.append([a, b, c0, c1])
+                return out
+            loc, rem = clip(work["local"]), clip(work["remote"])
+            if loc:
+                t += run(loc, symmetric, True)
+            if rem:
+                t += run(rem, False, False)
+            torch.cuda.synchronize()
+            done[g] = True
+            checkpoint.groups_run += 1
+            checkpoint.save(panel.cpu().numpy(), done, (r_lo, r_hi), n_qubits, symmetric, size)
+            if checkpoint.abort_after is not None and checkpoint.groups_run >= checkpoint.abort_after:
+                raise KeyboardInterrupt("checkpoint test: interrupted after %d row groups" % checkpoint.groups_run)
         return t
 
     if use_lane or use_big:
@@ -621,6 +693,8 @@ def _build_gram_general(comm, plan_factory, n_qubits, X, Y, chi_cap, device, ret
     if rank == 0:
         out = K if return_device else K.cpu().numpy()
     torch.cuda.synchronize()
+    if checkpoint is not None:
+        checkpoint.remove()          # complete: like the reference (cpu:326)
     prof["pair_seconds"] = None
     prof["total_s"] = time.perf_counter() - t_all
     prof["no_converge"] = 0   # a sweep-limit hit raises above (on every rank)

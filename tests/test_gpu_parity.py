@@ -633,3 +633,33 @@ def test_high_bond_dimension_against_statevector(qk, cuda_device, backend):
     Kt = mod.build_kernel_matrix(SingleComm(), ans, X, Y, truncation_error=1e-16, **kw)
     assert np.abs(Kt - oracle.statevector_gram(n, r, g, emap, X, Y)).max() < TOL
     assert int(prof["info_x"]["chi"].max()) <= 128          # chain-centre bound 2^7
+
+
+def test_checkpoint_resume(qk, cuda_device, tmp_path, monkeypatch):
+    """SURVEY.md 8(f)-3 (reference cpu:212-233,252-253,279-282,326): the CPU-backend entry point checkpoints its row
+    panel after every row group; a run interrupted after 2 of 4 groups leaves the file behind, the restarted run
+    computes only the 2 missing groups, returns the same matrix as an uninterrupted run, and removes the file."""
+    from cpu_backend.kernel_state_ansatz import KernelStateAnsatz, build_kernel_matrix
+    from qkmps.engine import SingleComm
+    monkeypatch.chdir(tmp_path)
+    n, r, g, d, N = 12, 2, 0.7, 2, 41
+    emap = oracle.entanglement_graph(n, d)
+    X = oracle.synthetic_features(N, n, 0)
+    Y = oracle.synthetic_features(17, n, 1)
+    ans = KernelStateAnsatz(n, r, g, emap)
+    for Yarg in (None, Y):
+        Kfull = build_kernel_matrix(SingleComm(), ans, X, Yarg, info_file="ck", truncation_error=1e-16)
+        assert build_kernel_matrix.last_checkpoint.groups_run == 4
+        ck = tmp_path / "tmp" / "checkpoint_rank_0_ck.npz"
+        assert not ck.exists()
+        build_kernel_matrix._abort_after = 2
+        with pytest.raises(KeyboardInterrupt):
+            build_kernel_matrix(SingleComm(), ans, X, Yarg, info_file="ck", truncation_error=1e-16)
+        build_kernel_matrix._abort_after = None
+        assert ck.exists() and np.load(ck)["done"].tolist() == [True, True, False, False]
+        K = build_kernel_matrix(SingleComm(), ans, X, Yarg, info_file="ck", truncation_error=1e-16)
+        assert build_kernel_matrix.last_checkpoint.groups_run == 2           # only the missing groups
+        assert not ck.exists()
+        assert np.array_equal(K, Kfull)
+        ref = oracle.statevector_gram(n, r, g, emap, X, Yarg) if Yarg is not None else oracle.statevector_gram(n, r, g, emap, X)
+        assert np.abs(K - ref).max() < TOL
