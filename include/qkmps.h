@@ -126,6 +126,9 @@ int qk_simulate_trace(const qk_plan* plan, int device, const double* x_host, int
                       int max_ops, qk_batch** out);
 /* last stage-1 kernel time in ms (CUDA events on the launching stream) */
 int qk_batch_sim_ms(const qk_batch* batch, float* ms);
+/* OR of the QK_FLAG_* bits (bit 0: bond cap hit, bit 1: Jacobi sweep limit) of every state of the batch; waits
+ * for the stage-1 kernel */
+int qk_batch_flags(const qk_batch* batch, int32_t* flags_or);
 /* seconds each datapoint's circuit took inside the kernel (clock64 around the datapoint; N doubles): the
  * per-circuit times the reference records around every simulate() call (gpu_backend/kernel_state_ansatz.py:220-222)
  * and reports as median / quartiles (:299-316) */

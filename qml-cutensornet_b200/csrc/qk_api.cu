@@ -394,6 +394,16 @@ int qk_batch_sim_ms(const qk_batch* b, float* ms) {
   return QK_OK;
 }
 
+static int batch_flags_or(const qk_batch* b, int* flags_or);
+// OR of the stage-1 flags of every state (QK_FLAG_*): the cheap correctness read-back after an asynchronous launch
+int qk_batch_flags(const qk_batch* b, int32_t* flags_or) {
+  if (!b || !flags_or) return fail(QK_ERR_ARG, "NULL argument");
+  int f = 0;
+  int rc = batch_flags_or(b, &f);
+  *flags_or = f;
+  return rc;
+}
+
 int qk_batch_unit_seconds(const qk_batch* b, double* seconds) {
   if (!b || !seconds) return fail(QK_ERR_ARG, "NULL argument");
   if (b->N == 0) return QK_OK;
@@ -401,8 +411,13 @@ int qk_batch_unit_seconds(const qk_batch* b, double* seconds) {
   if (b->ev1) QK_CUDA(cudaEventSynchronize(b->ev1), "stage-1 kernel");
   std::vector<long long> clk(b->N, 0);
   if (b->unit_clk) QK_CUDA(cudaMemcpy(clk.data(), b->unit_clk, clk.size() * sizeof(long long), cudaMemcpyDeviceToHost), "copy clocks");
-  int khz = 0;
-  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, b->device);
+  // cudaDevAttrClockRate is a slow query (milliseconds; worse while nvidia-smi polls the device): ask once per device
+  static int khz_cache[64] = {0};
+  int khz = (b->device >= 0 && b->device < 64) ? khz_cache[b->device] : 0;
+  if (khz == 0) {
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, b->device);
+    if (b->device >= 0 && b->device < 64) khz_cache[b->device] = khz;
+  }
   const double hz = khz > 0 ? 1e3 * khz : 1.965e9;
   for (int i = 0; i < b->N; ++i) seconds[i] = (double)clk[i] / hz;
   return QK_OK;

@@ -105,7 +105,9 @@ def build_kernel_matrix(mpi_comm, ansatz, X, Y=None, info_file=None, truncation_
     K, prof = build_gram(mpi_comm, plan_factory, n_qubits, np.asarray(X), None if Y is None else np.asarray(Y),
                          chi_cap=cap0, structural_cap=(cap0 >= bound))
 
-    if rank == root:
+    # The profiling dictionary needs per-state read-backs (bond dimensions, fidelities, per-circuit clocks); it is only
+    # assembled when somebody will see it (the reference always writes it: main.py passes info_file)
+    if rank == root and (info_file is not None or loglevel <= 20):
         ix, iy = prof["info_x"], prof["info_y"]
         sim_s = (prof["sim_ms_x"] + prof["sim_ms_y"]) * 1e-3
         # per-circuit times: clock64 around every datapoint inside the stage-1 kernel (rank 0's shard) -- the

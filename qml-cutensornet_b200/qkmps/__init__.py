@@ -63,7 +63,7 @@ EXPORTS = [
     "qk_batch_import", "qk_batch_max_chi", "qk_batch_destroy", "qk_frag_stride", "qk_batch_pack",
     "qk_batch_pack_scatter",
     "qk_gram_frags", "qk_batch_store", "qk_gram_lane", "qk_gram_store", "qk_gram_host", "qk_dmma_peak", "qk_pipe_mix", "qk_gram_big", "qk_batch_repack", "qk_simulate_async", "qk_batch_unit_seconds", "qk_batch_pack_async",
-    "qk_gram_set_tile_clocks", "qk_gram_tile_clocks_used",
+    "qk_gram_set_tile_clocks", "qk_gram_tile_clocks_used", "qk_batch_flags",
 ]
 
 _lib = None
@@ -205,6 +205,11 @@ class Batch:
         ms = ctypes.c_float()
         _check(lib().qk_batch_sim_ms(self._h, ctypes.byref(ms)))
         return ms.value
+
+    def flags_or(self) -> int:
+        out = ctypes.c_int32()
+        _check(lib().qk_batch_flags(self._h, ctypes.byref(out)))
+        return out.value
 
     def unit_seconds(self) -> np.ndarray:
         """Seconds every datapoint's circuit took inside the stage-1 kernel (per-unit timing)."""

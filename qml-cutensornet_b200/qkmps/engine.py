@@ -287,6 +287,42 @@ def _gather_panels(comm, panel, n_rows, n_cols, per_rows, symmetric, torch):
     return K
 
 
+class Profile(dict):
+    """Profile of one build_gram call.  Entries that need a device read-back (per-state bond dimensions, fidelities,
+    per-circuit and per-product times) are produced on first access, so a caller that only wants K pays nothing."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self._lazy = {}
+
+    def lazy(self, key, fn):
+        self._lazy[key] = fn
+
+    def __missing__(self, key):
+        if key in self._lazy:
+            self[key] = self._lazy.pop(key)()
+            return self[key]
+        raise KeyError(key)
+
+    def get(self, key, default=None):
+        try:
+            return self[key]
+        except KeyError:
+            return default
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or key in self._lazy
+
+
+_CLOCK_HZ = {}
+
+
+def _clock_hz(torch, device):
+    if device not in _CLOCK_HZ:
+        _CLOCK_HZ[device] = 1e3 * getattr(torch.cuda.get_device_properties(device), "clock_rate", 1.965e6)
+    return _CLOCK_HZ[device]
+
+
 class Checkpoint:
     """Per-rank checkpoint of the Gram row panel (replaces cpu_backend/kernel_state_ansatz.py:212-233,252-253,279-282,326
     of the reference: a per-rank ``tmp/checkpoint_rank_<rank>_<info_file>.npy`` rewritten after every tile, a tile
@@ -358,8 +394,7 @@ def _tile_clock_stats(clk, used, torch, device):
     ticks = ticks[ticks > 0]
     if not len(ticks):
         return None
-    hz = 1e3 * getattr(torch.cuda.get_device_properties(device), "clock_rate", 1.965e6)
-    return ticks / hz / 8.0
+    return ticks / _clock_hz(torch, device) / 8.0
 
 
 def _build_gram_streamlined(comm, plan_factory, n_qubits, X, Y, chi_cap, device, return_device, torch):
@@ -373,6 +408,10 @@ def _build_gram_streamlined(comm, plan_factory, n_qubits, X, Y, chi_cap, device,
     Ny = Nx if symmetric else len(Y)
     nb = n_qubits + 1
     t_all = time.perf_counter()
+    trace = []
+
+    def mark(name):
+        trace.append((name, (time.perf_counter() - t_all) * 1e3))
     main = torch.cuda.current_stream()
     stream = main.cuda_stream
     prof = {}
@@ -386,10 +425,13 @@ def _build_gram_streamlined(comm, plan_factory, n_qubits, X, Y, chi_cap, device,
     fragX = torch.empty(size * max(per_x, 1) * stride, dtype=torch.uint8, device=dev)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 
+    mark("alloc")
     xt = _to_device(X[lo:hi], device, n_qubits, torch)
     bx = simulate_async(plan, xt.data_ptr(), int(xt.shape[0]), int(xt.shape[1]) if xt.shape[0] else n_qubits,
                         device=device, stream=stream)
+    mark("simulate queued")
     bx.pack_async(D, fragX.data_ptr(), rank * per_x, stream)
+    mark("pack queued")
     launches = 2
     by, fragY, ylo, yhi = None, None, lo, hi
     if not symmetric:
@@ -425,6 +467,7 @@ def _build_gram_streamlined(comm, plan_factory, n_qubits, X, Y, chi_cap, device,
                    work["local"], symmetric, k_ptr, Nx, stream, wait=False,
                    tile_clocks=(clk.data_ptr(), n_tiles_max) if clk is not None else None)
         launches += 1
+    mark("local gram queued")
     ev[1].record(main)
     if gathered is not None:
         main.wait_event(gathered)
@@ -434,28 +477,36 @@ def _build_gram_streamlined(comm, plan_factory, n_qubits, X, Y, chi_cap, device,
                    Nx if symmetric else yhi, work["remote"], False, k_ptr, Nx, stream, wait=False)
         launches += 1
     ev[3].record(main)
+    mark("remote gram queued")
     K = _gather_panels(comm, panel, Ny, Nx, max(per_rows, 1), symmetric, torch)
+    mark("panels gathered (queued)")
     out = None
     if rank == 0:
         out = K if return_device else K.cpu().numpy()
     torch.cuda.synchronize()
+    mark("device idle")
 
-    info_x = bx.info()
-    info_x["seconds"] = bx.unit_seconds()
-    info_y = None
-    if by is not None:
-        info_y = by.info()
-        info_y["seconds"] = by.unit_seconds()
-    for inf in (info_x, info_y):
-        if inf is not None and len(inf["flags"]):
-            if np.any(inf["flags"] & QK_FLAG_NO_CONVERGE):
+    # correctness first: one small read-back of the stage-1 flags (anything else of the profile is read on demand)
+    for bb in (bx, by):
+        if bb is not None and bb.N:
+            fl = bb.flags_or()
+            if fl & QK_FLAG_NO_CONVERGE:
                 raise QkError(-2, "stage 1: the Jacobi SVD hit its sweep limit on at least one state")
-            if np.any(inf["flags"] & QK_FLAG_CAP_HIT):
+            if fl & QK_FLAG_CAP_HIT:
                 raise QkError(-3, "a state exceeded a bond cap that was declared structural")
+    mark("flags checked")
+
+    def full_info(bb):
+        inf = bb.info()
+        inf["seconds"] = bb.unit_seconds()
+        return inf
+    prof = Profile(prof)
+    prof.lazy("info_x", lambda: full_info(bx))
+    prof.lazy("info_y", (lambda: full_info(by)) if by is not None else (lambda: None))
+    prof["_keep"] = (bx, by, clk)
     prof["sim_ms_x"] = bx.sim_ms()
     prof["sim_ms_y"] = by.sim_ms() if by is not None else 0.0
     prof["chi_cap"] = chi_cap
-    prof["info_x"], prof["info_y"] = info_x, info_y
     prof["plan"] = plan.info()
     prof["plan_obj"] = plan
     prof["stage1_schedule"] = ("parallel (B form, one CTA cluster per datapoint)" if parallel
@@ -474,8 +525,11 @@ def _build_gram_streamlined(comm, plan_factory, n_qubits, X, Y, chi_cap, device,
     prof["Dx"], prof["Dy"] = D, D
     prof["launches"] = launches
     prof["mode"] = "streamlined"
-    prof["pair_seconds"] = _tile_clock_stats(clk, n_tiles_max, torch, device)
+    mark("events")
+    prof.lazy("pair_seconds", lambda: _tile_clock_stats(clk, n_tiles_max, torch, device))
     prof["no_converge"] = 0
+    mark("profile read back")
+    prof["host_trace_ms"] = trace
     prof["total_s"] = time.perf_counter() - t_all
     return out, prof
 
