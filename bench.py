@@ -544,7 +544,12 @@ def run_ours(args):
         "config": workload_config(args.workload),
         "details": {"packed_state_bytes": [int(v) for v in prof["frag_bytes_per_state"]],
                     "parallelism": f"datapoints sharded over {world} GPU(s); {prof.get('exchange', 'all-gather of packed states')}",
-                    "stage1_schedule": prof.get("stage1_schedule", ""), "stage2_kernel": gk},
+                    "stage1_schedule": prof.get("stage1_schedule", ""), "stage2_kernel": gk,
+                    "engine_mode": prof.get("mode", ""),
+                    "rank0_last_step": {"gram_ms_local": prof.get("gram_ms_local"), "gram_ms_remote": prof.get("gram_ms_remote"),
+                                        "exchange_wait_ms": prof.get("exchange_wait_ms"),
+                                        "host_trace_ms": [[a, round(b, 3)] for a, b in (prof.get("host_trace_ms") or [])]},
+                    "step_ms_rank0": [round(v, 3) for v in step_ms]},
         "circuits_per_s": (N + M) / (ms_per_step * 1e-3),
         "stage_ms": {"simulate": sim_mean, "gram": gram_mean, "other": ms_per_step - sim_mean - gram_mean,
                      "note": "kernel times on their own streams; stages may overlap, so 'other' can be negative"},
