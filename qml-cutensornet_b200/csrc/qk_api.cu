@@ -309,10 +309,9 @@ static int simulate_impl(const qk_plan* plan, int device, cudaStream_t stream, c
     }
   } else if (plan->parallel) {
     what = "stage-1 kernel (B form)";
-    // CTAs per datapoint: 8 for small shards, 4 for mid-sized ones (measured, engine.py); the host says which through
-    // QK_SIM_CLUSTER_AUTO, QK_SIM_CLUSTER overrides (experiments)
+    // CTAs per datapoint: 8 for small batches, 4 for mid-sized ones (measured, profiles/r02_stage1_schedules.txt);
+    // QK_SIM_CLUSTER overrides (experiments)
     int ncta = N <= 150 ? 8 : 4;
-    if (const char* ev = getenv("QK_SIM_CLUSTER_AUTO")) { const int v = atoi(ev); if (v >= 1 && v <= 8) ncta = v; }
     if (const char* ev = getenv("QK_SIM_CLUSTER")) { const int v = atoi(ev); if (v >= 1 && v <= 8) ncta = v; }
     double* lam_dev = nullptr; int32_t* lvl_dev = nullptr; QkStat* parts_dev = nullptr;
     e = salloc((void**)&lam_dev, (size_t)N * (plan->n + 1) * P.lam_ld * sizeof(double));

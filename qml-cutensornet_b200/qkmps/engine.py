@@ -29,11 +29,7 @@ from . import (CHI_LIMIT, DMMA_D_LIMIT, QK_FLAG_CAP_HIT, QK_FLAG_NO_CONVERGE, Qk
 # (C3 shape, paired distance-2 routing, profiles/r02_stage1_schedules.txt), stage-1 ms sequential | B form by cluster size:
 #   125 points:  9.8 | c4 6.6  c5 5.6  c6 5.0  c8 4.8        250 points:  9.8 | c4 8.6  c5 10.5  c6 9.6  c8 8.9
 #   500 points: 11.1 | c2 15.5  c4 15.6                      1000 points: 15.0 | c2 27.1  c4 29.1
-PARALLEL_MAX_LOCAL = 300
-
-
-def parallel_cluster(n_local: int) -> int:
-    return 8 if n_local <= 150 else 4
+PARALLEL_MAX_LOCAL = 300   # cluster size: 8 CTAs up to 150 datapoints, 4 above (chosen in qk_api.cu from the batch size)
 LANE_CHI_LIMIT = 4   # at or below this bond dimension stage 2 runs one lane per pair on the FP64 CUDA cores
 FRAG_D_LIMIT = 32    # padded bond dimension up to which stage 2 runs on the packed-fragment kernels
 # bond caps tried in turn; each has its own kernel configuration: <= 32 shared-memory-resident kernels (one CTA or, in
@@ -193,10 +189,7 @@ class ShardStates:
 
 def _use_parallel(comm, n_local):
     env = os.environ.get("QK_SCHEDULE", "")
-    use = (env == "parallel") or (env == "" and comm.Get_size() > 1 and 0 < n_local <= PARALLEL_MAX_LOCAL)
-    if use and "QK_SIM_CLUSTER" not in os.environ:
-        os.environ["QK_SIM_CLUSTER_AUTO"] = str(parallel_cluster(n_local))   # read by libqkmps at launch time
-    return use
+    return (env == "parallel") or (env == "" and comm.Get_size() > 1 and 0 < n_local <= PARALLEL_MAX_LOCAL)
 
 
 def _to_device(X_shard, device, n_qubits, torch):
