@@ -169,7 +169,19 @@ def cpu_reference_sample(workload, budget_s=14.0, cores=None, mode="pytket"):
 
 
 # --------------------------------------------------------------------------------------- parity
-def parity_reference(workload, n_states, mode="pytket"):
+def parity_reference_cached(workload, n_states):
+    """tests/golden/parity_ref_<workload>.npz (written by tests/golden/make_parity_refs.py with this very function's
+    uncached twin) if it was made for the same workload tuple and sample size; else run the oracle now."""
+    f = ROOT / "tests" / "golden" / f"parity_ref_{workload}.npz"
+    if f.exists():
+        z = np.load(f)
+        if np.array_equal(z["workload"], np.array(WORKLOADS[workload], dtype=np.float64)) and int(z["n_states"]) == n_states:
+            return {"sx": z["sx"], "sy": z["sy"] if len(z["sy"]) else None, "overlap": z["overlap"],
+                    "chi_itensors": z["chi_itensors"], "sx_itensors": z["sx_itensors"], "cached": str(f.name)}
+    return parity_reference(workload, n_states)
+
+
+def parity_reference(workload, n_states, mode="pytket", n_itensors=8):
     """Oracle side of the parity check (run on rank 0 BEFORE CUDA is initialised: fork pool).  Simulates
     `n_states` states spread over the whole dataset (so that every rank's shard is represented) with the GPU arm's
     truncation rule, and all overlaps among them; plus their ITensors-rule bond dimensions."""
@@ -184,7 +196,7 @@ def parity_reference(workload, n_states, mode="pytket"):
     jobs = [(n, gates, X[i], TRUNC_ERROR, mode) for i in sx]
     if M:
         jobs += [(n, gates, Y[i], TRUNC_ERROR, mode) for i in sy]
-    jobs_it = [(n, gates, X[i], TRUNC_ERROR, "itensors") for i in sx[:8]]
+    jobs_it = [(n, gates, X[i], TRUNC_ERROR, "itensors") for i in sx[:n_itensors]]
     ctx = mp.get_context("fork")
     with ctx.Pool(min(P, len(jobs)), initializer=_cpu_worker_init) as pool:
         res = pool.map(_cpu_sim_one, jobs + jobs_it)
@@ -198,7 +210,7 @@ def parity_reference(workload, n_states, mode="pytket"):
     else:
         ov = np.array([[inner_prepared(prep[a][1], prep[b][0], prep[b][2]) for b in range(nx)] for a in range(nx)])
     chi_it = np.array([[1] + [t.shape[2] for t in ts] for ts in tens_it], dtype=np.int32)
-    return {"sx": sx, "sy": sy, "overlap": ov, "chi_itensors": chi_it, "sx_itensors": sx[:8]}
+    return {"sx": sx, "sy": sy, "overlap": ov, "chi_itensors": chi_it, "sx_itensors": sx[:n_itensors]}
 
 
 def parity_check(K, ref, workload, qkmps, ans, device, capx, slab_rows=64):
@@ -210,7 +222,7 @@ def parity_check(K, ref, workload, qkmps, ans, device, capx, slab_rows=64):
     Ks = K[np.ix_(sy if M else sx, sx)]
     abs_err = float(np.abs(Ks - Kref).max())
     rel = np.abs(Ks - Kref) / np.maximum(Kref, 1e-300)
-    out = {"max_abs_err": abs_err, "tol_abs": PARITY_TOL, "n_checked": int(Ks.size),
+    out = {"max_abs_err": abs_err, "tol_abs": PARITY_TOL, "n_checked": int(Ks.size), "oracle_fixture": ref.get("cached"),
            "oracle": f"numpy restatement, pytket rule, {len(sx)}{' x ' + str(len(sy)) if M else ''} sampled states "
                      "(all their pairs)",
            "max_rel_err_vs_oracle": float(rel.max()), "median_rel_err_vs_oracle": float(np.median(rel)),
@@ -386,7 +398,7 @@ def run_ours(args):
     if rank == 0 and not args.no_cpu_baseline:
         cpu_base = cpu_reference_sample(args.workload, budget_s=args.cpu_budget)
     if rank == 0 and args.parity_states > 0:
-        pref = parity_reference(args.workload, args.parity_states)
+        pref = parity_reference_cached(args.workload, args.parity_states)
 
     import torch
     import qkmps
@@ -435,7 +447,7 @@ def run_ours(args):
     def step_e2e():
         return build_kernel_matrix(comm, ans, X, Y, truncation_error=TRUNC_ERROR, chi=cap0)
 
-    warm = max(args.warmup, 3)
+    warm = max(args.warmup, args.min_warmup)
     for _ in range(warm):
         step_device()
         step_e2e()
@@ -569,6 +581,8 @@ def run_ours(args):
         "max_chi": int(chi_x.max()), "mean_max_chi": float(chi_x.max(axis=1).mean()),
         "parity": parity,
     }
+    if warm < 3:
+        line["warmup_below_contract"] = True
     if cpu_base is not None:
         line["cpu_baseline"] = {k: cpu_base[k] for k in ("value", "unit", "cores", "kind", "sample")}
         line["cpu_baseline"]["circuits_per_s"] = cpu_base["circuits_per_s"]
@@ -589,6 +603,8 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=14.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parity-states", type=int, default=32, help="states the oracle simulates for the parity check (0: off)")
+    ap.add_argument("--min-warmup", type=int, default=3, help="floor for --warmup (the timing contract asks for >= 3; lower only "
+                    "for exploratory runs of the heavy c4 workloads -- the JSON line then says so)")
     ap.add_argument("--chi", type=int, default=0, help="first bond cap tried (0: the backend's own choice)")
     ap.add_argument("--points", type=int, default=0, help="override the number of datapoints (experiments only)")
     args = ap.parse_args()
