@@ -597,7 +597,10 @@ def _build_gram_general(comm, plan_factory, n_qubits, X, Y, chi_cap, device, ret
     Dx = pad_dims(red[:nb])
     Dy = Dx if symmetric else pad_dims(red[nb:2 * nb])
     max_chi = int(red[:2 * nb].max())
-    cap_common = int(red[-1])
+    # layout of the exchanged stores: the smallest cap of the ladder that covers the measured bond dimensions (a shard
+    # may have been simulated with a far larger cap -- above 32 a generous cap costs stage 1 nothing, but the
+    # exchanged buffer is sized by it)
+    cap_common = next((c for c in CAP_LADDER if c >= max_chi), int(red[-1]))
     use_lane = (max_chi <= LANE_CHI_LIMIT and int(red[-2]) == 0 and os.environ.get("QK_GRAM_LANE", "1") != "0")
     use_big = (not use_lane) and (int(max(Dx.max(), Dy.max())) > FRAG_D_LIMIT or os.environ.get("QK_GRAM_BIG", "0") == "1")
     stream = torch.cuda.current_stream().cuda_stream

@@ -21,7 +21,8 @@ def main():
     rank, size = comm.Get_rank(), comm.Get_size()
     worst = 0.0
     kernels = set()
-    for (n, r, g, d, nx, ny) in [(10, 2, 0.5, 1, 40, 13), (12, 2, 0.7, 2, 37, 9), (14, 2, 0.1, 2, 21, 21), (10, 3, 0.5, 4, 10, 6)]:
+    for (n, r, g, d, nx, ny) in [(10, 2, 0.5, 1, 40, 13), (12, 2, 0.7, 2, 37, 9), (14, 2, 0.1, 2, 21, 21), (10, 3, 0.5, 4, 10, 6),
+                                   (14, 4, 1.0, 4, 11, 5)]:      # bond dimension up to 128: large-matrix stage 1 + batched GEMMs
         emap = oracle.entanglement_graph(n, d)
         X = oracle.synthetic_features(nx, n, 0)
         Y = oracle.synthetic_features(ny, n, 1)
@@ -79,7 +80,7 @@ def main():
         assert big < 1e-8, big
         assert worst < 1e-8, worst
         # both stage-2 paths were exercised across ranks: stores (chi <= 4) and packed fragments
-        assert {"qk_gram_lane_kernel", "qk_gram_dmma_kernel"} <= kernels, kernels
+        assert {"qk_gram_lane_kernel", "qk_gram_dmma_kernel", "qk_big_gemm_kernel"} <= kernels, kernels
         print(f"MULTI_GPU_OK ranks={size} max_err={worst:.3e} max_err_baseline_shapes={big:.3e}")
 
 
