@@ -149,3 +149,68 @@ def test_gloo_ranks(world):
         p.join(timeout=180)
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     assert out.get(timeout=5) == "ok"
+
+
+class _FileBcastComm:
+    """mpi4py-like communicator for the test below: rank / size + a pickled bcast through a file (what the engine needs
+    from a real ``MPI.COMM_WORLD`` to bootstrap torch.distributed)."""
+
+    def __init__(self, rank, size, path):
+        self.rank, self.size, self.path = rank, size, path
+
+    def Get_rank(self):
+        return self.rank
+
+    def Get_size(self):
+        return self.size
+
+    def bcast(self, obj, root=0):
+        import pickle
+        import time
+        if self.rank == root:
+            with open(self.path + ".tmp", "wb") as f:
+                pickle.dump(obj, f)
+            os.replace(self.path + ".tmp", self.path)
+            return obj
+        for _ in range(600):
+            if os.path.exists(self.path):
+                with open(self.path, "rb") as f:
+                    return pickle.load(f)
+            time.sleep(0.05)
+        raise TimeoutError("bcast")
+
+
+def _worker_mpi_like(rank, world, path, out):
+    import sys
+    import pathlib
+    root = pathlib.Path(__file__).resolve().parent.parent
+    for p in (root, root / "qml-cutensornet_b200", root / "tests"):
+        sys.path.insert(0, str(p))
+    for v in ("RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        os.environ.pop(v, None)
+    import torch
+    from qkmps.comm import TorchComm, allreduce_max_int
+    from qkmps.engine import _as_torch_comm
+    comm = _as_torch_comm(_FileBcastComm(rank, world, path))       # what build_gram does with a foreign communicator
+    assert isinstance(comm, TorchComm) and comm.Get_rank() == rank and comm.Get_size() == world
+    assert allreduce_max_int(comm, rank + 10) == world + 9
+    comm.Barrier()
+    if rank == 0:
+        out.put("ok")
+    torch.distributed.destroy_process_group()
+
+
+def test_mpi_like_communicator_bootstraps_torch_distributed(tmp_path):
+    """A communicator that is not a TorchComm (mpi4py's COMM_WORLD with one process per GPU) is accepted at size > 1:
+    the rendezvous address travels through its bcast."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    path = str(tmp_path / "bcast.pkl")
+    procs = [ctx.Process(target=_worker_mpi_like, args=(r, 2, path, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert out.get(timeout=5) == "ok"
