@@ -146,6 +146,9 @@ int qk_batch_export(const qk_batch* batch, int i, void* host_buf, int64_t buf_by
 int qk_batch_import(int device, int n_qubits, int N, const int32_t* chi /*[N][n+1]*/,
                     const void* host_tensors, int64_t bytes, qk_batch** out);
 int qk_batch_max_chi(const qk_batch* batch, int32_t* max_chi /*[n+1]*/);
+/* Frees the batch's working store (its site tensors) in stream order once they have been packed / exchanged; bond
+ * dimensions, fidelities, flags and per-datapoint times stay readable, export / pack / repack then fail with QK_ERR_ARG */
+int qk_batch_release_store(qk_batch* batch, void* stream);
 void qk_batch_destroy(qk_batch* batch);
 
 /* ---- exchange format: replaces pickled MPS send/recv/sendrecv

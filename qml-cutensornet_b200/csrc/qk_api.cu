@@ -383,6 +383,21 @@ int qk_simulate_trace(const qk_plan* plan, int device, const double* x_host, int
   return rc;
 }
 
+// Hands the working store (the bulk of a batch's memory) back in stream order once it has been packed / exchanged;
+// bond dimensions, statistics and per-datapoint clocks stay readable.
+int qk_batch_release_store(qk_batch* b, void* stream_v) {
+  if (!b) return fail(QK_ERR_ARG, "NULL batch");
+  if (b->store) {
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(b->device);
+    pool_free_after(b->store, (cudaStream_t)stream_v);
+    cudaSetDevice(prev);
+    b->store = nullptr;
+  }
+  return QK_OK;
+}
+
 int qk_batch_sim_ms(const qk_batch* b, float* ms) {
   if (!b || !ms) return fail(QK_ERR_ARG, "NULL argument");
   *ms = b->sim_ms;
@@ -464,6 +479,7 @@ int qk_batch_info(const qk_batch* b, int32_t* chi, double* fidelity, double* tru
 int qk_batch_export(const qk_batch* b, int i, void* host_buf, int64_t buf_bytes) {
   if (!b || !host_buf) return fail(QK_ERR_ARG, "NULL argument");
   if (i < 0 || i >= b->N) return fail(QK_ERR_ARG, "state index out of range");
+  if (!b->store) return fail(QK_ERR_ARG, "the batch's store was released");
   QK_CUDA(cudaSetDevice(b->device), "cudaSetDevice");
   std::vector<int32_t> c(b->n + 1);
   QK_CUDA(cudaMemcpy(c.data(), b->chi + (size_t)i * (b->n + 1), c.size() * sizeof(int32_t), cudaMemcpyDeviceToHost), "copy chi");
@@ -554,6 +570,7 @@ int qk_batch_pack_scatter(const qk_batch* b, const int32_t* D, void* frag_dev, c
   int rc = check_D(b->n, D);
   if (rc != QK_OK) return rc;
   if (b->N == 0) return QK_OK;
+  if (!b->store) return fail(QK_ERR_ARG, "the batch's store was released");
   QK_CUDA(cudaSetDevice(b->device), "cudaSetDevice");
   cudaStream_t stream = (cudaStream_t)stream_v;
   // bond dimensions of the states that are actually packed must fit the padded dims
@@ -592,6 +609,7 @@ int qk_batch_pack_async(const qk_batch* b, const int32_t* D, void* frag_dev, int
   int rc = check_D(b->n, D);
   if (rc != QK_OK) return rc;
   if (b->N == 0) return QK_OK;
+  if (!b->store) return fail(QK_ERR_ARG, "the batch's store was released");
   for (int s = 0; s <= b->n; ++s)
     if (D[s] < b->cap[s]) return fail(QK_ERR_ARG, "asynchronous pack needs padded dimensions >= the batch's bond caps");
   QK_CUDA(cudaSetDevice(b->device), "cudaSetDevice");
@@ -771,6 +789,7 @@ int qk_gram_store(const qk_batch* X, const qk_batch* Y, double* K_host, int64_t 
   if (!X || !K_host) return fail(QK_ERR_ARG, "NULL argument");
   if (!Y) Y = X;
   if (X->n != Y->n || X->device != Y->device) return fail(QK_ERR_ARG, "batches do not match");
+  if ((X->N && !X->store) || (Y->N && !Y->store)) return fail(QK_ERR_ARG, "a batch's store was released");
   if (ldk < X->N) return fail(QK_ERR_ARG, "ldk must be >= Nx");
   if (X->N == 0 || Y->N == 0) return QK_OK;
   QK_CUDA(cudaSetDevice(X->device), "cudaSetDevice");
@@ -957,6 +976,7 @@ int qk_batch_repack(const qk_batch* b, const qk_plan* plan, void* store_dev, int
   if (!b || !plan || !store_dev || !chi_dev) return fail(QK_ERR_ARG, "NULL argument");
   if (b->n != plan->n) return fail(QK_ERR_ARG, "batch and plan differ in the number of qubits");
   if (b->N == 0) return QK_OK;
+  if (!b->store) return fail(QK_ERR_ARG, "the batch's store was released");
   QK_CUDA(cudaSetDevice(b->device), "cudaSetDevice");
   cudaStream_t stream = (cudaStream_t)stream_v;
   int64_t* off_dev = nullptr; int32_t* dst_dev = nullptr;

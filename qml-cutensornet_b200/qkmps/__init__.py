@@ -63,7 +63,7 @@ EXPORTS = [
     "qk_batch_import", "qk_batch_max_chi", "qk_batch_destroy", "qk_frag_stride", "qk_batch_pack",
     "qk_batch_pack_scatter",
     "qk_gram_frags", "qk_batch_store", "qk_gram_lane", "qk_gram_store", "qk_gram_host", "qk_dmma_peak", "qk_pipe_mix", "qk_gram_big", "qk_batch_repack", "qk_simulate_async", "qk_batch_unit_seconds", "qk_batch_pack_async",
-    "qk_gram_set_tile_clocks", "qk_gram_tile_clocks_used", "qk_batch_flags",
+    "qk_gram_set_tile_clocks", "qk_gram_tile_clocks_used", "qk_batch_flags", "qk_batch_release_store",
 ]
 
 _lib = None
@@ -205,6 +205,10 @@ class Batch:
         ms = ctypes.c_float()
         _check(lib().qk_batch_sim_ms(self._h, ctypes.byref(ms)))
         return ms.value
+
+    def release_store(self, stream: int = 0):
+        """Give the site tensors' memory back (stream-ordered); bond dimensions and statistics stay readable."""
+        _check(lib().qk_batch_release_store(self._h, ctypes.c_void_p(stream)))
 
     def flags_or(self) -> int:
         out = ctypes.c_int32()

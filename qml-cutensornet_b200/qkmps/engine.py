@@ -433,6 +433,7 @@ def _build_gram_streamlined(comm, plan_factory, n_qubits, X, Y, chi_cap, device,
                         device=device, stream=stream)
     mark("simulate queued")
     bx.pack_async(D, fragX.data_ptr(), rank * per_x, stream)
+    bx.release_store(stream)        # only the packed fragments are needed from here on
     mark("pack queued")
     launches = 2
     by, fragY, ylo, yhi = None, None, lo, hi
@@ -443,6 +444,7 @@ def _build_gram_streamlined(comm, plan_factory, n_qubits, X, Y, chi_cap, device,
                             device=device, stream=stream)
         fragY = torch.empty(max(yhi - ylo, 1) * stride, dtype=torch.uint8, device=dev)   # bras are only needed locally
         by.pack_async(D, fragY.data_ptr(), 0, stream)
+        by.release_store(stream)
         launches += 2
     gathered = None
     if size > 1:
