@@ -31,7 +31,9 @@ from . import (CHI_LIMIT, DMMA_D_LIMIT, QK_FLAG_CAP_HIT, QK_FLAG_NO_CONVERGE, Qk
 #   500 points: 11.1 | c2 15.5  c4 15.6                      1000 points: 15.0 | c2 27.1  c4 29.1
 PARALLEL_MAX_LOCAL = 300   # cluster size: 8 CTAs up to 150 datapoints, 4 above (chosen in qk_api.cu from the batch size)
 LANE_CHI_LIMIT = 4   # at or below this bond dimension stage 2 runs one lane per pair on the FP64 CUDA cores
-FRAG_D_LIMIT = 32    # padded bond dimension up to which stage 2 runs on the packed-fragment kernels
+FRAG_D_LIMIT = 16    # padded bond dimension up to which stage 2 runs on the packed-fragment tensor-core kernel; above it the
+#                      batched-GEMM sweep on the stores is faster than the CUDA-core fragment kernel (C4 shape at gamma 0.1,
+#                      chi <= 17, 32 896 pairs x 165 sites: 48 ms against 119 ms)
 # bond caps tried in turn; each has its own kernel configuration: <= 32 shared-memory-resident kernels (one CTA or, in
 # B form, one small cluster per datapoint), above that the large-matrix kernel (theta in L2, block Jacobi, one CTA
 # cluster per datapoint -- BASELINE config 4)

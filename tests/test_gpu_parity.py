@@ -338,9 +338,9 @@ def test_full_size_config3_properties(qk, cuda_device):
 
 
 def test_large_bond_dimension_path(qk, cuda_device):
-    """Bond dimensions above 16 (here up to ~32): cap escalation 16 -> 24 -> 32 in stage 1 and the generic
-    overlap kernel on the packed buffers in stage 2, through the reference-facing entry point (ITensors rule:
-    the pytket rule keeps rounding-noise values and would ask for more than the 32 the kernels hold)."""
+    """Bond dimensions above 16 (here up to ~32): cap escalation 16 -> 24 -> 32 in stage 1 and the batched-GEMM
+    sweep on the stores in stage 2, through the reference-facing entry point; the CUDA-core kernel on packed
+    fragments (qk_gram_frags with 16 < D <= 32) is checked on the same states through the C ABI."""
     from cpu_backend.kernel_state_ansatz import KernelStateAnsatz, build_kernel_matrix
     from qkmps.engine import SingleComm
     n, r, g, d = 10, 3, 0.5, 4      # 10 qubits: bond dimension structurally <= 32
@@ -350,9 +350,18 @@ def test_large_bond_dimension_path(qk, cuda_device):
     ans = KernelStateAnsatz(n, r, g, emap)
     K = build_kernel_matrix(SingleComm(), ans, X, info_file="/tmp/qk_big", truncation_error=1e-16)
     prof = build_kernel_matrix.last_profile
-    assert prof["info_x"]["chi"].max() > 16 and prof["gram_kernel"] == "qk_gram_frag_generic_kernel"
+    assert prof["info_x"]["chi"].max() > 16 and prof["gram_kernel"] == "qk_big_gemm_kernel"
     assert np.abs(K - oracle.statevector_gram(n, r, g, emap, X)).max() < TOL
     assert np.array_equal(K, K.T)
+    import torch
+    batch = qk.simulate(_plan(qk, ans, 0, 32), X)
+    D = qk.pad_dims(batch.max_chi())
+    assert 16 < D.max() <= 32
+    frag = torch.zeros(len(X) * qk.frag_stride(n, D), dtype=torch.uint8, device="cuda")
+    batch.pack(D, frag.data_ptr())
+    Kf = torch.zeros((len(X), len(X)), dtype=torch.float64, device="cuda")
+    qk.gram_frags(0, n, D, frag.data_ptr(), len(X), D, frag.data_ptr(), len(X), [[0, len(X), 0, len(X)]], 1, Kf.data_ptr(), len(X))
+    assert np.abs(Kf.cpu().numpy() - K).max() < 1e-10
     Kt = build_kernel_matrix(SingleComm(), ans, X, Y, info_file="/tmp/qk_big", truncation_error=1e-16)
     assert np.abs(Kt - oracle.statevector_gram(n, r, g, emap, X, Y)).max() < TOL
 
