@@ -127,7 +127,7 @@ def test_published_chi_range():
 
 def test_golden_fixtures():
     """tests/golden/*.npz were written by tests/golden/make_golden.py (oracle + exact statevector)."""
-    files = sorted(GOLDEN.glob("*.npz"))
+    files = sorted(GOLDEN.glob("c*.npz")) + sorted((pathlib.Path(__file__).parent / "golden").glob("d*.npz"))
     assert files, "golden fixtures missing"
     for f in files:
         z = np.load(f)
