@@ -284,6 +284,7 @@ static int simulate_impl(const qk_plan* plan, int device, cudaStream_t stream, c
   P.abs_rel = 0.0;
   P.parallel = plan->parallel; P.lam = nullptr; P.lam_ld = plan->rmax / 2; P.level_start = nullptr; P.n_levels = 0;
   P.big_w = nullptr; P.big_s = nullptr; P.big_w_stride = P.big_s_stride = 0; P.big_flag = nullptr; P.big_jb = plan->jb;
+  P.big_wb_entries = (int)qk_big_wb_entries(plan->rmax, plan->jb);
   P.unit_clk = b->unit_clk;
 
   if ((e = cudaEventCreate(&b->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");

@@ -322,7 +322,6 @@ int qk_compile_plan(int n, const qk_gate* gates_in, int n_gates, int trunc_mode,
     plan->threads = 256;
     plan->jb = 8;
     if (const char* e = getenv("QK_BIG_JB")) { const int v = atoi(e); if (v >= 1 && v <= 16) plan->jb = v; }   // tests
-    while (plan->jb > 1 && (size_t)plan->rmax * 2 * plan->jb * sizeof(c128) > (size_t)144 * 1024) plan->jb /= 2;
     plan->smem_bytes = qk_big_smem_bytes(n, plan->rmax, plan->jb, plan->threads);
   }
   return QK_OK;

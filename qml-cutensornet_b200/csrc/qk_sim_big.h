@@ -44,7 +44,7 @@ QK_DEV int qk_ld_flag(const int* p) { return *p; }
 
 QK_HD size_t qk_big_smem_bytes(int n, int rmax, int jb, int G) {
   const int capmax = rmax / 2;
-  size_t b = (size_t)rmax * 2 * jb * sizeof(c128);                    // Wb: one pair of column blocks
+  size_t b = qk_big_wb_entries(rmax, jb) * sizeof(c128);              // Wb: one pair of column blocks
   b += (size_t)4 * (G > capmax ? G : capmax) * sizeof(c128);          // ef
   b += (size_t)4 * G * sizeof(double);                                // scr
   b += (size_t)rmax * sizeof(double);                                 // nrm2
@@ -61,7 +61,7 @@ QK_DEV void qk_big_carve(SimCtx& c, const SimParams* P, unsigned char* smem, int
   const int rmax = P->rmax, capmax = rmax / 2, jb = P->big_jb;
   c.P = P;
   c.Wb = (c128*)smem;
-  c.ef = c.Wb + (size_t)rmax * 2 * jb;
+  c.ef = c.Wb + qk_big_wb_entries(rmax, jb);
   c.scr = (double*)(c.ef + 4 * (G > capmax ? G : capmax));
   c.nrm2 = c.scr + 4 * G;
   c.gate = (c128*)(c.nrm2 + rmax + (rmax & 1));
@@ -119,7 +119,9 @@ QK_DEV void qk_big_jacobi(SimCtx& c, int R, int C) {
   c128* W = c.W;
   c128* Wb = c.Wb;
   const int ldw = R;
-  const int jb = c.P->big_jb;
+  int jb = c.P->big_jb;                                      // columns per block: what fits for this row count
+  if ((size_t)2 * jb * R > (size_t)c.P->big_wb_entries) jb = (int)((size_t)c.P->big_wb_entries / ((size_t)2 * R));
+  if (jb < 1) jb = 1;
   const double tol2 = c.P->tol * c.P->tol;
   // total weight, computed identically by every CTA
   QK_PAR_BEGIN(tid)
@@ -159,7 +161,7 @@ QK_DEV void qk_big_jacobi(SimCtx& c, int R, int C) {
               Wb[i] = qk_ld(W + (size_t)src * ldw + row);
             }
           QK_PAR_END
-          qk_jacobi_sweep<G>(c, Wb, R, R, nc, tol2, floor2, abs2);
+          qk_jacobi_sweep<G, true>(c, Wb, R, R, nc, tol2, floor2, abs2);
           QK_PAR_BEGIN(tid)
             for (int i = tid; i < R * nc; i += G) {
               const int col = i / R, row = i - col * R;

@@ -339,7 +339,8 @@ __device__ __forceinline__ void qk_pair_step_generic(c128* wp, c128* wq, int R, 
 // One sweep (every round of the round-robin tournament) of one-sided Jacobi on the R x C matrix W (column-major,
 // leading dimension ldw).  Sets c.sh->rotated when a rotation above QK_QUAD_EPS was applied.  Shared by the
 // shared-memory-resident path (qk_jacobi) and the column-block visits of the large-matrix path (qk_sim_big.h).
-template <int G>
+// WIDE: the caller has the register budget for 16 rows of both columns per thread (large-matrix kernel, one CTA per SM).
+template <int G, bool WIDE = false>
 QK_DEV void qk_jacobi_sweep(SimCtx& c, c128* W, int ldw, int R, int C, double tol2, double floor2, double abs2) {
   const int Ce = (C + 1) & ~1;
   const int npairs = Ce / 2;
@@ -365,6 +366,7 @@ QK_DEV void qk_jacobi_sweep(SimCtx& c, c128* W, int ldw, int R, int C, double to
         else if (rpt <= 2) qk_pair_step<2>(wp, wq, R, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
         else if (rpt <= 4) qk_pair_step<4>(wp, wq, R, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
         else if (rpt <= 8 && G != 128) qk_pair_step<8>(wp, wq, R, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
+        else if (WIDE && rpt <= 16) qk_pair_step<16>(wp, wq, R, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
         else qk_pair_step_generic(wp, wq, R, sl, tpp, valid, tol2, floor2, abs2, &c.sh->rotated);
       QK_PAR_END
 #else

@@ -111,6 +111,20 @@ struct SimParams {
   c128* big_s;               // [n_clusters][big_s_stride]   staging of the recovered factor, capmax * rmax entries
   int64_t big_w_stride, big_s_stride;
   int* big_flag;             // [n_clusters][2] "a rotation happened in this sweep", alternating slots
-  int big_jb;                // columns per block of the block Jacobi
+  int big_jb;                // columns per block of the block Jacobi (upper limit; per SVD: what fits, below)
+  int big_wb_entries;        // c128 entries of the shared-memory buffer for one pair of column blocks
   long long* unit_clk;       // optional [N]: clock64 ticks each datapoint took (per-unit timing), or NULL
 };
+
+#include <stddef.h>
+// c128 entries of the shared-memory buffer that holds one pair of column blocks: room for 2 jb columns of 2 cap rows,
+// but never more than 128 KB.  The block size of an SVD is chosen from its ACTUAL row count (qk_big_jacobi), so a
+// generous bond cap does not shrink the blocks of the matrices that actually occur.
+QK_HD size_t qk_big_wb_entries(int rmax, int jb) {
+  size_t e = (size_t)rmax * 2 * jb;
+  const size_t lim = (size_t)128 * 1024 / sizeof(c128);
+  if (e > lim) e = lim;
+  if (e < (size_t)rmax * 2) e = (size_t)rmax * 2;                     // at least one column per block
+  return e;
+}
+

@@ -69,6 +69,7 @@ long long qk_emu_simulate(int n, const qk_gate* gates, int n_gates, int trunc_mo
   std::vector<c128> big_w, big_s;
   std::vector<int> big_flag(4, 0);
   P.big_w = nullptr; P.big_s = nullptr; P.big_w_stride = P.big_s_stride = 0; P.big_flag = nullptr; P.big_jb = plan.jb;
+  P.big_wb_entries = (int)qk_big_wb_entries(plan.rmax, plan.jb);
   P.unit_clk = nullptr;
   if (plan.big) {
     big_w.resize((size_t)plan.rmax * plan.rmax);
