@@ -375,8 +375,11 @@ def run_reference(args):
     last, vals, ests = None, [], []
     for _ in range(args.warmup):
         cpu_reference_sample(args.workload, budget_s=3.0)
+    # every step is a bounded sample of the workload; the per-step budget shrinks with K so that the whole run stays
+    # within a few minutes
+    budget = min(args.cpu_budget, max(3.0, 150.0 / max(args.steps, 1)))
     for _ in range(args.steps):
-        last = cpu_reference_sample(args.workload, budget_s=args.cpu_budget)
+        last = cpu_reference_sample(args.workload, budget_s=budget)
         vals.append(last["value"]); ests.append(last["est_job_s"])
     v = float(np.mean(vals))
     line = {
