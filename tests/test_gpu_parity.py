@@ -672,3 +672,43 @@ def test_checkpoint_resume(qk, cuda_device, tmp_path, monkeypatch):
         assert np.array_equal(K, Kfull)
         ref = oracle.statevector_gram(n, r, g, emap, X, Yarg) if Yarg is not None else oracle.statevector_gram(n, r, g, emap, X)
         assert np.abs(K - ref).max() < TOL
+
+
+def test_engine_modes_agree_and_async_abi(qk, cuda_device, monkeypatch):
+    """The streamlined engine mode (everything queued asynchronously, padded dims from the bond caps, row panel +
+    max(K, K^T) assembly) and the general mode (cap escalation, measured dims) give the same matrix; the asynchronous
+    C entry points behave as documented (results usable on the stream at once, store released in stream order)."""
+    import torch
+    from gpu_backend.kernel_state_ansatz import build_kernel_matrix
+    from qkmps.engine import SingleComm
+    n, r, g, d, N = 50, 2, 1.0, 2, 45
+    X = oracle.synthetic_features(N, n, 0)
+    Y = oracle.synthetic_features(14, n, 1)
+    ans = _ansatz(n, r, g, d)
+    for Yarg in (None, Y):
+        K1 = build_kernel_matrix(SingleComm(), ans, X, Yarg, truncation_error=1e-16)
+        assert build_kernel_matrix.last_profile["mode"] == "streamlined"
+        monkeypatch.setenv("QK_ENGINE", "general")
+        K2 = build_kernel_matrix(SingleComm(), ans, X, Yarg, truncation_error=1e-16)
+        assert build_kernel_matrix.last_profile["mode"] == "general"
+        monkeypatch.delenv("QK_ENGINE")
+        assert K1.shape == K2.shape and np.abs(K1 - K2).max() < 1e-12
+    prof = build_kernel_matrix.last_profile
+    assert prof["info_x"]["chi"].shape == (N, n + 1) and prof["info_x"]["seconds"].min() > 0      # lazy read-back works
+    # asynchronous ABI
+    plan = _plan(qk, ans, 1, 16)
+    xd = torch.from_numpy(X).cuda()
+    s = torch.cuda.current_stream().cuda_stream
+    b = qk.simulate_async(plan, xd.data_ptr(), N, n, device=0, stream=s)
+    D = qk.pad_dims(np.minimum(16, 2 ** np.minimum(np.arange(n + 1), n - np.arange(n + 1)).clip(max=30)))
+    frag = torch.zeros(N * qk.frag_stride(n, D), dtype=torch.uint8, device="cuda")
+    b.pack_async(D, frag.data_ptr(), 0, s)
+    b.release_store(s)
+    Kd = torch.zeros((N, N), dtype=torch.float64, device="cuda")
+    qk.gram_frags(0, n, D, frag.data_ptr(), N, None, None, N, [[0, N, 0, N]], 1, Kd.data_ptr(), N, s, wait=False)
+    torch.cuda.synchronize()
+    assert b.flags_or() == 0 and b.sim_ms() > 0 and b.unit_seconds().min() > 0
+    assert np.abs(Kd.cpu().numpy() - build_kernel_matrix(SingleComm(), ans, X, truncation_error=1e-16)).max() < 1e-12
+    with pytest.raises(qk.QkError):
+        b.pack(D, frag.data_ptr())            # the store is gone
+    assert b.info()["chi"].max() <= 16        # ... the bond dimensions are not
