@@ -72,7 +72,7 @@ _lib = None
 def build(force: bool = False) -> pathlib.Path:
     """Compile libqkmps.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
     srcs = [CSRC / f for f in ("qk_api.cu", "qk_sim.cu", "qk_gram.cu", "qk_plan.cpp", "qk_types.h",
-                               "qk_sim_core.h", "qk_plan.h", "qk_kernels.cuh")]
+                               "qk_sim_core.h", "qk_sim_big.h", "qk_plan.h", "qk_kernels.cuh")]
     srcs.append(_HERE.parent.parent / "include" / "qkmps.h")
     stale = force or not LIB_PATH.exists() or any(s.stat().st_mtime > LIB_PATH.stat().st_mtime for s in srcs)
     if stale:
