@@ -223,3 +223,23 @@ def test_ansatz_mirror_matches_oracle_and_reference_errors():
         c.circuit_for_data([0.1])
     assert structural_chi_bound(50, 2, oracle.entanglement_graph(50, 2)) == 16
     assert structural_chi_bound(20, 2, oracle.entanglement_graph(20, 1)) == 4
+
+
+def test_header_is_plain_c_and_matches_the_library(qk, tmp_path):
+    """include/qkmps.h is the drop-in boundary: it must compile as C99 (no C++ or torch types in the signatures), and a
+    C program that references every declared function must link against libqkmps.so."""
+    import re
+    import subprocess
+    root = pathlib.Path(__file__).resolve().parent.parent
+    hdr = (root / "include" / "qkmps.h").read_text()
+    names = sorted(set(re.findall(r"\b(qk_[a-z0-9_]+)\s*\(", hdr)) - {"qk_plan_create"})
+    assert set(names) == set(qk.EXPORTS), (set(names) ^ set(qk.EXPORTS))
+    src = tmp_path / "use_abi.c"
+    src.write_text('#include "qkmps.h"\n#include <stdio.h>\ntypedef void (*fn_t)(void);\nint main(void) {\n  fn_t f[] = {'
+                   + ", ".join(f"(fn_t){n}" for n in names) +
+                   '};\n  printf("%d %d\\n", (int)(sizeof(f) / sizeof(f[0])), qk_version());\n  return 0;\n}\n')
+    exe = tmp_path / "use_abi"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", f"-I{root / 'include'}", str(src), "-o", str(exe),
+                           str(qk.LIB_PATH), f"-Wl,-rpath,{qk.LIB_PATH.parent}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.split() == [str(len(names)), str(qk.lib().qk_version())]

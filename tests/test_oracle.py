@@ -140,3 +140,22 @@ def test_golden_fixtures():
             assert np.abs(K - z["K_exact"]).max() < 1e-8, f.name
         chi = np.array([[1] + m.bond_dims() + [1] for m in simulate_batch(n, r, g, emap, z["X"])])
         assert np.array_equal(chi, z["chi_X"]), f.name
+
+
+def test_pytket_rule_sums_in_one_order():
+    """The pytket-rule restatement compares a running sum with the total accumulated in the same (largest-first) order,
+    so it stops as soon as the remaining values no longer change the sum: rounding-noise values are not kept, a tail
+    whose members each move the sum is."""
+    from oracle.mps_ref import truncate_pytket
+    s = np.array([1.0] + [1e-9] * 200)                    # squares 1e-18 each: below half an ulp of the sum
+    k, kept = truncate_pytket(s, 1.0 - 1e-16)
+    assert k == 1 and kept == 1.0
+    s = np.array([1.0, 3e-8, 2e-8, 1e-9])                 # squares 9e-16 and 4e-16 move the sum, 1e-18 does not
+    k, kept = truncate_pytket(s, 1.0 - 1e-16)
+    assert k == 3
+    k, kept = truncate_pytket(np.array([1.0, 0.5, 1e-17]), 1.0 - 1e-16)      # below value_of_zero: trimmed by the SVD itself
+    assert k == 2
+    k, kept = truncate_pytket(np.array([2.0, 1.0, 1.0, 0.5]), 1.0 - 0.2)       # looser fidelity: smallest prefix reaching 0.8
+    assert k == 2 and abs(kept - 5.0 / 6.25) < 1e-15
+    k, kept = truncate_pytket(np.array([2.0, 1.0, 1.0, 0.5]), 1.0 - 1e-16, chi=2)
+    assert k == 2
